@@ -1,0 +1,1056 @@
+// bsm_api.cu — C ABI (include/bsm.h) over the sm_100a kernels: device handles, upload/download
+// with format conversion, kernel dispatch heuristics, sharding helpers, generators.
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bsm_common.cuh"
+#include "kernels.h"
+
+namespace bsm {
+
+static Runtime g_rt;
+static thread_local std::string g_err;
+static thread_local bsm_launch_info g_info;
+static std::atomic<uint64_t> g_launches{0};
+
+Runtime &rt() { return g_rt; }
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int status, const std::string &msg)
+{
+    g_err = msg;
+    return status;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int ensure_init()
+{
+    if (g_rt.device >= 0) return BSM_OK;
+    return bsm_init(0);
+}
+
+static int dev_alloc(void **p, size_t bytes)
+{
+    BSM_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    return BSM_OK;
+}
+
+static inline uint64_t pad4(uint64_t n) { return (n + 3) / 4 * 4; }
+
+// leading dimension of library-owned dense buffers: rows start 16-byte aligned whenever a row is
+// at least 16 bytes, so lanes can use 128-bit loads
+static uint64_t default_ld(uint64_t cols, int dtype)
+{
+    const uint64_t v = 16 / dtype_size(dtype);
+    if (cols <= 1) return cols ? cols : 1;
+    return round_up(cols, v);
+}
+
+static int alloc_csr(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, bsm_csr **out)
+{
+    if (rows >= 0xFFFFFFF0ull || cols >= 0xFFFFFFF0ull || nnz >= 0xFFFFFFF0ull)
+        return fail(BSM_ERR_INDEX_OVERFLOW, "rows, cols and nnz must fit the device's u32 indices");
+    bsm_csr *a = new bsm_csr();
+    a->dtype = dtype;
+    a->rows = rows;
+    a->cols = cols;
+    a->nnz = nnz;
+    const size_t s = dtype_size(dtype);
+    int st = dev_alloc(&a->vals, (pad4(nnz) + 4) * s);
+    if (st == BSM_OK) st = dev_alloc((void **)&a->col_idx, (pad4(nnz) + 4) * 4);
+    if (st == BSM_OK) st = dev_alloc((void **)&a->row_ptr, (pad4(rows + 1) + 4) * 4);
+    if (st != BSM_OK) {
+        bsm_csr_free(a);
+        return st;
+    }
+    // defined padding (TMA over-reads up to the next multiple of 4 entries)
+    cudaStream_t sm = g_rt.stream;
+    cudaMemsetAsync((char *)a->vals + nnz * s, 0, (pad4(nnz) + 4 - nnz) * s, sm);
+    cudaMemsetAsync(a->col_idx + nnz, 0, (pad4(nnz) + 4 - nnz) * 4, sm);
+    cudaMemsetAsync(a->row_ptr + rows + 1, 0, (pad4(rows + 1) + 4 - rows - 1) * 4, sm);
+    *out = a;
+    return BSM_OK;
+}
+
+static int compute_stats(bsm_csr *a)
+{
+    uint32_t *d = nullptr;
+    BSM_CUDA(cudaMallocAsync(&d, 8, g_rt.stream));
+    BSM_CUDA(cudaMemsetAsync(d, 0, 8, g_rt.stream));
+    BSM_TRY(launch_row_stats(a->row_ptr, a->rows, d, d + 1, g_rt.stream));
+    uint32_t h[2] = {0, 0};
+    BSM_CUDA(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, g_rt.stream));
+    BSM_CUDA(cudaFreeAsync(d, g_rt.stream));
+    BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
+    if (h[1]) return fail(BSM_ERR_INVALID_ARGUMENT, "row_index is not non-decreasing");
+    a->max_row_nnz = h[0];
+    return BSM_OK;
+}
+
+template <typename T>
+static int csr_upload_rows(int dtype, uint64_t rows_total, uint64_t cols, const T *v, const uint64_t *col_index,
+                           const uint64_t *row_index, uint64_t row_begin, uint64_t row_end, bsm_csr **out)
+{
+    BSM_TRY(ensure_init());
+    if (!out || !row_index || row_begin > row_end || row_end > rows_total)
+        return fail(BSM_ERR_INVALID_ARGUMENT, "csr_upload: bad arguments");
+    const uint64_t e0 = row_index[row_begin], e1 = row_index[row_end];
+    if (e1 < e0) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_upload: row_index is not non-decreasing");
+    const uint64_t nnz = e1 - e0, rows = row_end - row_begin;
+    if (nnz && (!v || !col_index)) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_upload: null value/index arrays");
+    bsm_csr *a = nullptr;
+    BSM_TRY(alloc_csr(dtype, rows, cols, nnz, &a));
+    cudaStream_t sm = g_rt.stream;
+    uint64_t *stage = nullptr;
+    uint32_t *flags = nullptr;
+    const uint64_t stage_elems = std::max<uint64_t>(nnz, rows + 1);
+    int st = BSM_OK;
+    auto body = [&]() -> int {
+        BSM_CUDA(cudaMalloc(&stage, stage_elems * 8));
+        BSM_CUDA(cudaMalloc(&flags, 8));
+        BSM_CUDA(cudaMemsetAsync(flags, 0, 8, sm));
+        if (nnz) {
+            BSM_CUDA(cudaMemcpyAsync(a->vals, v + e0, nnz * sizeof(T), cudaMemcpyHostToDevice, sm));
+            // usize -> u32 narrowing and the column bound check happen on the device
+            BSM_CUDA(cudaMemcpyAsync(stage, col_index + e0, nnz * 8, cudaMemcpyHostToDevice, sm));
+            BSM_TRY(launch_narrow_u64(stage, a->col_idx, nnz, cols, 0, flags, sm));
+        }
+        BSM_CUDA(cudaMemcpyAsync(stage, row_index + row_begin, (rows + 1) * 8, cudaMemcpyHostToDevice, sm));
+        BSM_TRY(launch_narrow_u64(stage, a->row_ptr, rows + 1, nnz + 1, e0, flags + 1, sm));
+        uint32_t h[2] = {0, 0};
+        BSM_CUDA(cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, sm));
+        BSM_CUDA(cudaStreamSynchronize(sm));
+        if (h[0]) return fail(BSM_ERR_OUT_OF_BOUNDS, "csr_upload: a col_index is >= cols");
+        if (h[1]) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_upload: row_index entry outside [0,nnz]");
+        return compute_stats(a);
+    };
+    st = body();
+    if (stage) cudaFree(stage);
+    if (flags) cudaFree(flags);
+    if (st != BSM_OK) {
+        bsm_csr_free(a);
+        return st;
+    }
+    *out = a;
+    return BSM_OK;
+}
+
+template <typename T>
+static int csr_upload(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const T *v, const uint64_t *col_index,
+                      const uint64_t *row_index, uint64_t row_index_len, bsm_csr **out)
+{
+    // a finalised reference Csr has row_index.len() == rows+1 and *row_index.last() == nnz
+    // (src/sparse.rs:206-219, 162-164)
+    if (row_index_len != rows + 1)
+        return fail(BSM_ERR_NOT_FINALISED, "csr_upload: row_index must have rows+1 entries (call finalise() first)");
+    if (!row_index) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_upload: null row_index");
+    if (row_index[0] != 0 || row_index[rows] != nnz)
+        return fail(BSM_ERR_INVALID_ARGUMENT, "csr_upload: row_index must start at 0 and end at nnz");
+    return csr_upload_rows<T>(dtype, rows, cols, v, col_index, row_index, 0, rows, out);
+}
+
+template <typename T> static int csr_download(const bsm_csr *a, int dtype, T *v, uint64_t *col_index, uint64_t *row_index)
+{
+    BSM_TRY(ensure_init());
+    if (!a) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_download: null handle");
+    if (a->dtype != dtype) return fail(BSM_ERR_DTYPE_MISMATCH, "csr_download: dtype mismatch");
+    cudaStream_t sm = g_rt.stream;
+    uint64_t *stage = nullptr;
+    const uint64_t stage_elems = std::max<uint64_t>(a->nnz, a->rows + 1);
+    BSM_CUDA(cudaMalloc(&stage, stage_elems * 8));
+    int st = [&]() -> int {
+        if (a->nnz) {
+            BSM_CUDA(cudaMemcpyAsync(v, a->vals, a->nnz * sizeof(T), cudaMemcpyDeviceToHost, sm));
+            BSM_TRY(launch_widen_u32(a->col_idx, stage, a->nnz, sm));
+            BSM_CUDA(cudaMemcpyAsync(col_index, stage, a->nnz * 8, cudaMemcpyDeviceToHost, sm));
+        }
+        BSM_TRY(launch_widen_u32(a->row_ptr, stage, a->rows + 1, sm));
+        BSM_CUDA(cudaMemcpyAsync(row_index, stage, (a->rows + 1) * 8, cudaMemcpyDeviceToHost, sm));
+        BSM_CUDA(cudaStreamSynchronize(sm));
+        return BSM_OK;
+    }();
+    cudaFree(stage);
+    return st;
+}
+
+static int dense_alloc(int dtype, uint64_t rows, uint64_t cols, bsm_dense **out)
+{
+    BSM_TRY(ensure_init());
+    if (!out) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_alloc: null out");
+    if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "dense_alloc: dtype must be f32 or f64");
+    if (rows >= 0xFFFFFFF0ull || cols >= 0xFFFFFFF0ull) return fail(BSM_ERR_INDEX_OVERFLOW, "dense dims must fit u32");
+    bsm_dense *d = new bsm_dense();
+    d->dtype = dtype;
+    d->rows = rows;
+    d->cols = cols;
+    d->ld = default_ld(cols, dtype);
+    const size_t bytes = (size_t)rows * d->ld * dtype_size(dtype);
+    int st = dev_alloc(&d->data, bytes + 16);
+    if (st != BSM_OK) {
+        delete d;
+        return st;
+    }
+    if (d->ld != cols && bytes) cudaMemsetAsync(d->data, 0, bytes, g_rt.stream);   // defined padding columns
+    *out = d;
+    return BSM_OK;
+}
+
+constexpr uint64_t kColGroup = 32;   // columns staged per transpose step
+
+template <typename T> static int dense_upload(int dtype, uint64_t rows, uint64_t cols, const T *const *col_ptrs, bsm_dense **out)
+{
+    BSM_TRY(ensure_init());
+    if (cols && !col_ptrs) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_upload: null column pointers");
+    bsm_dense *d = nullptr;
+    BSM_TRY(dense_alloc(dtype, rows, cols, &d));
+    cudaStream_t sm = g_rt.stream;
+    T *stage = nullptr;
+    int st = [&]() -> int {
+        if (rows == 0 || cols == 0) return BSM_OK;
+        const uint64_t g = std::min<uint64_t>(kColGroup, cols);
+        BSM_CUDA(cudaMalloc(&stage, g * rows * sizeof(T)));
+        for (uint64_t c0 = 0; c0 < cols; c0 += g) {
+            const uint64_t gc = std::min<uint64_t>(g, cols - c0);
+            for (uint64_t c = 0; c < gc; ++c) {
+                if (!col_ptrs[c0 + c]) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_upload: null column");
+                BSM_CUDA(cudaMemcpyAsync(stage + c * rows, col_ptrs[c0 + c], rows * sizeof(T), cudaMemcpyHostToDevice, sm));
+            }
+            // column-major Vec<Vec<T>> (src/dense.rs:5-9) -> row-major device layout
+            BSM_TRY(launch_transpose_cm2rm(dtype, stage, (T *)d->data + c0, rows, gc, d->ld, sm));
+        }
+        BSM_CUDA(cudaStreamSynchronize(sm));
+        return BSM_OK;
+    }();
+    if (stage) cudaFree(stage);
+    if (st != BSM_OK) {
+        bsm_dense_free(d);
+        return st;
+    }
+    *out = d;
+    return BSM_OK;
+}
+
+template <typename T> static int dense_download(const bsm_dense *d, int dtype, T *const *col_ptrs)
+{
+    BSM_TRY(ensure_init());
+    if (!d) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_download: null handle");
+    if (d->dtype != dtype) return fail(BSM_ERR_DTYPE_MISMATCH, "dense_download: dtype mismatch");
+    if (d->rows == 0 || d->cols == 0) return BSM_OK;
+    if (!col_ptrs) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_download: null column pointers");
+    cudaStream_t sm = g_rt.stream;
+    T *stage = nullptr;
+    const uint64_t g = std::min<uint64_t>(kColGroup, d->cols);
+    BSM_CUDA(cudaMalloc(&stage, g * d->rows * sizeof(T)));
+    int st = [&]() -> int {
+        for (uint64_t c0 = 0; c0 < d->cols; c0 += g) {
+            const uint64_t gc = std::min<uint64_t>(g, d->cols - c0);
+            BSM_TRY(launch_transpose_rm2cm(dtype, (const T *)d->data + c0, stage, d->rows, gc, d->ld, sm));
+            for (uint64_t c = 0; c < gc; ++c)
+                BSM_CUDA(cudaMemcpyAsync(col_ptrs[c0 + c], stage + c * d->rows, d->rows * sizeof(T), cudaMemcpyDeviceToHost, sm));
+            BSM_CUDA(cudaStreamSynchronize(sm));   // stage is reused by the next group
+        }
+        return BSM_OK;
+    }();
+    cudaFree(stage);
+    return st;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------
+static int pow2_ceil(int x)
+{
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// lane shape for `n` columns starting at byte-aligned pointers
+static Shape pick_shape(uint32_t n, uint64_t ldb, uint64_t ldc, uint64_t col0, const void *b, const void *c, size_t s,
+                        bool prefer_wide, uint64_t extra_ld = 0)
+{
+    Shape sh;
+    int V = (int)(16 / s);
+    auto ok = [&](int v) {
+        const uint64_t bytes = (uint64_t)v * s;
+        return n % v == 0 && ldb % v == 0 && ldc % v == 0 && col0 % v == 0 && (extra_ld % v == 0) &&
+               ((uintptr_t)b % bytes == 0) && ((uintptr_t)c % bytes == 0);
+    };
+    while (V > 1 && !ok(V)) V /= 2;
+    int L = (int)(n / V);
+    if (prefer_wide)
+        while (L < 32 && V > 1) {
+            V /= 2;
+            L = (int)(n / V);
+        }
+    sh.V = V;
+    if (L >= 32) {
+        sh.G = 32;
+        const int nt = (L + 31) / 32;
+        sh.NT = nt <= 1 ? 1 : (nt <= 2 ? 2 : 4);
+    } else {
+        sh.G = pow2_ceil(L);
+        sh.NT = 1;
+    }
+    return sh;
+}
+
+static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags)
+{
+    const size_t s = dtype_size(a->dtype);
+    const uint32_t n_total = (uint32_t)b->cols;
+    const int vmax = (int)(16 / s);
+    uint32_t tile = tn.col_tile > 0 ? (uint32_t)tn.col_tile : n_total;
+    tile = std::min<uint32_t>(tile, 32u * vmax * 4u);   // widest shape one pass can hold in registers
+    if (tile < n_total && tile % vmax) tile = std::max<uint32_t>(vmax, tile / vmax * vmax);
+    const double mean = a->rows ? (double)a->nnz / (double)a->rows : 0.0;
+    const int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 8) : 8;
+    int passes = 0;
+    g_info = bsm_launch_info();
+    g_info.algo = BSM_ALGO_VECTOR;
+    for (uint32_t col0 = 0; col0 < n_total; col0 += tile, ++passes) {
+        const uint32_t n = std::min(tile, n_total - col0);
+        const char *bp = (const char *)b->data + (size_t)col0 * s;
+        char *cp = (char *)c->data + (size_t)col0 * s;
+        Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows != 0);
+        const uint32_t rows_per_pass = (uint32_t)nw * (32u / sh.G);
+        RowParams p{};
+        p.row_ptr = a->row_ptr;
+        p.col_idx = a->col_idx;
+        p.vals = a->vals;
+        p.B = bp;
+        p.C = cp;
+        p.rows = (uint32_t)a->rows;
+        p.n = n;
+        p.ldb = (uint32_t)b->ld;
+        p.ldc = (uint32_t)c->ld;
+        // rows per TMA batch: enough entries per bulk copy to be efficient, small enough that the
+        // persistent CTAs stay a narrow front over the matrix
+        uint32_t rb;
+        if (tn.rows_per_batch > 0) {
+            rb = (uint32_t)tn.rows_per_batch;
+        } else {
+            const double target = (double)n * s <= 32.0 ? 2560.0 : 1024.0;
+            rb = (uint32_t)std::min<double>(4096.0, target / std::max(1.0, mean));
+        }
+        rb = std::max(rows_per_pass, rb / rows_per_pass * rows_per_pass);
+        rb = (uint32_t)round_up(rb, 4);
+        p.rb = rb;
+        p.rows_per_warp = (uint32_t)round_up((rb + nw - 1) / nw, 32u / sh.G);
+        p.num_batches = (uint32_t)((a->rows + rb - 1) / rb);
+        const double want = std::min<double>((double)rb * (double)a->max_row_nnz,
+                                             std::max(2.0 * rb * mean, rb * mean + 1024.0));
+        p.cap = (uint32_t)pad4((uint64_t)std::min<double>(want, 12288.0)) + 4;
+        p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
+        p.far_thr = (flags & BSM_TUNE_B_FAR_NOALLOC) ? (tn.far_threshold ? tn.far_threshold : 4096u) : 0u;
+        p.flags = flags;
+        size_t smem = row_kernel_smem_bytes(a->dtype, p);
+        while (smem > (size_t)g_rt.max_smem_optin - 1024 && p.stages > 1) {
+            --p.stages;
+            smem = row_kernel_smem_bytes(a->dtype, p);
+        }
+        if (smem > (size_t)g_rt.max_smem_optin - 1024) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: batch does not fit shared memory");
+        const int block = (nw + 1) * 32;
+        int occ = 0;
+        BSM_TRY(row_kernel_occupancy(a->dtype, sh, block, smem, &occ));
+        if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_vector: kernel does not fit on an SM");
+        int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
+        const int grid = (int)std::min<uint64_t>(p.num_batches, (uint64_t)g_rt.sm_count * ctas);
+        if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, grid, block, smem, g_rt.stream));
+        g_info.kernels += grid > 0;
+        g_info.vec_elems = sh.V;
+        g_info.lanes_per_row = sh.G;
+        g_info.reg_tiles = sh.NT;
+        g_info.grid = grid;
+        g_info.block = block;
+        g_info.smem_bytes = (int)smem;
+        g_info.rows_per_batch = (int)p.rb;
+        g_info.stages = (int)p.stages;
+        g_info.capacity = (int)p.cap;
+    }
+    g_info.passes = passes;
+    return BSM_OK;
+}
+
+static int ensure_partition(bsm_csr *a, uint32_t items, uint32_t num_chunks)
+{
+    if (a->part_rows && a->part_items == (int)items && a->part_chunks == num_chunks) return BSM_OK;
+    if (a->part_rows) cudaFree(a->part_rows);
+    a->part_rows = nullptr;
+    BSM_CUDA(cudaMalloc(&a->part_rows, ((size_t)num_chunks + 1) * 4));
+    BSM_TRY(launch_merge_partition(a->row_ptr, (uint32_t)a->rows, (uint32_t)a->nnz, items, num_chunks, a->part_rows, g_rt.stream));
+    g_info.kernels += 1;
+    a->part_items = (int)items;
+    a->part_chunks = num_chunks;
+    return BSM_OK;
+}
+
+static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags)
+{
+    bsm_csr *a = const_cast<bsm_csr *>(a_const);   // partition / carry caches live in the handle
+    const size_t s = dtype_size(a->dtype);
+    const uint32_t n_total = (uint32_t)b->cols;
+    const int vmax = (int)(16 / s);
+    uint32_t tile = tn.col_tile > 0 ? (uint32_t)tn.col_tile : n_total;
+    tile = std::min<uint32_t>(tile, 32u * vmax * 4u);
+    if (tile < n_total && tile % vmax) tile = std::max<uint32_t>(vmax, tile / vmax * vmax);
+    const uint64_t total = a->rows + a->nnz;
+    g_info = bsm_launch_info();
+    g_info.algo = BSM_ALGO_MERGE;
+    int passes = 0;
+    for (uint32_t col0 = 0; col0 < n_total; col0 += tile, ++passes) {
+        const uint32_t n = std::min(tile, n_total - col0);
+        const uint64_t ldcar = round_up(n, vmax);
+        Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows >= 0, ldcar);
+        const int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 8) : 8;
+        const int block = nw * 32;
+        const uint32_t groups = (uint32_t)nw * (32u / sh.G);
+        uint32_t items = tn.merge_items > 0 ? (uint32_t)tn.merge_items : (sh.G == 32 ? 256u : std::max(16u, 2048u / groups));
+        items = (uint32_t)round_up(items, 4);
+        if (total + items >= 0xFFFFFFF0ull) return fail(BSM_ERR_INDEX_OVERFLOW, "spmm_merge: rows+nnz must fit u32");
+        const uint32_t num_chunks = (uint32_t)((total + items - 1) / items);
+        if (num_chunks == 0) continue;
+        BSM_TRY(ensure_partition(a, items, num_chunks));
+        const size_t need_vals = (size_t)num_chunks * ldcar * s, need_rows = (size_t)num_chunks * 4;
+        if (a->carry_vals_bytes < need_vals) {
+            if (a->carry_vals) cudaFree(a->carry_vals);
+            a->carry_vals = nullptr;
+            a->carry_vals_bytes = 0;
+            BSM_CUDA(cudaMalloc(&a->carry_vals, need_vals));
+            a->carry_vals_bytes = need_vals;
+        }
+        if (a->carry_rows_bytes < need_rows) {
+            if (a->carry_rows) cudaFree(a->carry_rows);
+            a->carry_rows = nullptr;
+            a->carry_rows_bytes = 0;
+            BSM_CUDA(cudaMalloc(&a->carry_rows, need_rows));
+            a->carry_rows_bytes = need_rows;
+        }
+        MergeParams p{};
+        p.row_ptr = a->row_ptr;
+        p.col_idx = a->col_idx;
+        p.vals = a->vals;
+        p.B = (const char *)b->data + (size_t)col0 * s;
+        p.C = (char *)c->data + (size_t)col0 * s;
+        p.part_rows = a->part_rows;
+        p.carry_vals = a->carry_vals;
+        p.carry_rows = a->carry_rows;
+        p.rows = (uint32_t)a->rows;
+        p.nnz = (uint32_t)a->nnz;
+        p.n = n;
+        p.ldb = (uint32_t)b->ld;
+        p.ldc = (uint32_t)c->ld;
+        p.ldcar = (uint32_t)ldcar;
+        p.items = items;
+        p.num_chunks = num_chunks;
+        p.flags = flags;
+        const size_t smem = merge_kernel_smem_bytes(a->dtype, sh, block, items);
+        if (smem > (size_t)g_rt.max_smem_optin - 1024) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_merge: items do not fit shared memory");
+        int grid = 0;
+        BSM_TRY(launch_spmm_merge(a->dtype, sh, p, block, smem, g_rt.stream, &grid));
+        BSM_TRY(launch_merge_fixup(a->dtype, p, g_rt.stream));
+        g_info.kernels += 2;
+        g_info.vec_elems = sh.V;
+        g_info.lanes_per_row = sh.G;
+        g_info.reg_tiles = sh.NT;
+        g_info.grid = grid;
+        g_info.block = block;
+        g_info.smem_bytes = (int)smem;
+        g_info.merge_items = (int)items;
+        g_info.merge_chunks = (int)num_chunks;
+    }
+    g_info.passes = passes;
+    return BSM_OK;
+}
+
+static int choose_algo(const bsm_csr *a, int requested)
+{
+    if (requested == BSM_ALGO_VECTOR || requested == BSM_ALGO_MERGE) return requested;
+    // csr_row_stats heuristic: the vector kernel serialises a row on one lane group, so one row far
+    // above the mean (power-law hubs, the bench-as-written matrix) needs the nnz-balanced kernel
+    const double mean = a->rows ? (double)a->nnz / (double)a->rows : 0.0;
+    if ((double)a->max_row_nnz > 64.0 + 8.0 * mean) return BSM_ALGO_MERGE;
+    return BSM_ALGO_VECTOR;
+}
+
+static int spmm_dispatch(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning *tuning)
+{
+    BSM_TRY(ensure_init());
+    if (!a || !b || !c) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm: null handle");
+    // src/sparse.rs:427-429
+    if (a->cols != b->rows) return fail(BSM_ERR_INCORRECT_DIMENSIONS, "spmm: A.cols != B.rows (MatErr::IncorrectDimensions)");
+    if (c->rows != a->rows || c->cols != b->cols)
+        return fail(BSM_ERR_INCORRECT_DIMENSIONS, "spmm: C must be A.rows x B.cols");
+    if (a->dtype != b->dtype || a->dtype != c->dtype) return fail(BSM_ERR_DTYPE_MISMATCH, "spmm: dtype mismatch");
+    if (c->data == b->data && c->rows && c->cols) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm: C must not alias B");
+    bsm_tuning tn{};
+    if (tuning) tn = *tuning;
+    uint32_t flags = tn.flags ? (tn.flags & 0x7FFFFFFFu) : BSM_TUNE_DEFAULT_FLAGS;
+    g_info = bsm_launch_info();
+    if (a->rows == 0 || b->cols == 0) return BSM_OK;
+    const int algo = choose_algo(a, tn.algo);
+    if (algo == BSM_ALGO_MERGE) return spmm_merge(a, b, c, tn, flags);
+    return spmm_vector(a, b, c, tn, flags);
+}
+
+static int dense_to_csr_impl(const bsm_dense *d, bsm_csr **out)
+{
+    BSM_TRY(ensure_init());
+    if (!d || !out) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_to_csr: null argument");
+    cudaStream_t sm = g_rt.stream;
+    uint32_t *counts = nullptr;
+    unsigned long long *total = nullptr;
+    bsm_csr *r = nullptr;
+    int st = [&]() -> int {
+        BSM_CUDA(cudaMalloc(&counts, (pad4(d->rows + 1) + 4) * 4));
+        BSM_CUDA(cudaMalloc(&total, 8));
+        BSM_CUDA(cudaMemsetAsync(total, 0, 8, sm));
+        BSM_CUDA(cudaMemsetAsync(counts, 0, (pad4(d->rows + 1) + 4) * 4, sm));
+        BSM_TRY(launch_count_nonzero(d->dtype, d->data, d->rows, d->cols, d->ld, counts, total, sm));
+        BSM_TRY(exclusive_scan_u32(counts, counts, d->rows + 1, sm));   // row_index incl. the finalise() tail
+        unsigned long long h = 0;
+        BSM_CUDA(cudaMemcpyAsync(&h, total, 8, cudaMemcpyDeviceToHost, sm));
+        BSM_CUDA(cudaStreamSynchronize(sm));
+        BSM_TRY(alloc_csr(d->dtype, d->rows, d->cols, h, &r));
+        BSM_CUDA(cudaMemcpyAsync(r->row_ptr, counts, (d->rows + 1) * 4, cudaMemcpyDeviceToDevice, sm));
+        BSM_TRY(launch_scatter_nonzero(d->dtype, d->data, d->rows, d->cols, d->ld, r->row_ptr, r->vals, r->col_idx, sm));
+        r->max_row_nnz = d->cols;
+        BSM_CUDA(cudaStreamSynchronize(sm));
+        return BSM_OK;
+    }();
+    if (counts) cudaFree(counts);
+    if (total) cudaFree(total);
+    if (st != BSM_OK) {
+        if (r) bsm_csr_free(r);
+        return st;
+    }
+    *out = r;
+    return BSM_OK;
+}
+
+template <typename T>
+static int mul_dense_host(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const T *v, const uint64_t *col_index,
+                          const uint64_t *row_index, uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                          const T *const *rhs_col_ptrs, int algo, uint64_t *out_nnz, T **out_v, uint64_t **out_col_index,
+                          uint64_t **out_row_index)
+{
+    if (!out_nnz || !out_v || !out_col_index || !out_row_index) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense_host: null out");
+    if (cols != rhs_rows) return fail(BSM_ERR_INCORRECT_DIMENSIONS, "mul_dense: A.cols != rhs.rows (MatErr::IncorrectDimensions)");
+    bsm_csr *a = nullptr, *r = nullptr;
+    bsm_dense *b = nullptr, *c = nullptr;
+    T *hv = nullptr;
+    uint64_t *hc = nullptr, *hr = nullptr;
+    int st = [&]() -> int {
+        BSM_TRY(csr_upload<T>(dtype, rows, cols, nnz, v, col_index, row_index, row_index_len, &a));
+        BSM_TRY(dense_upload<T>(dtype, rhs_rows, rhs_cols, rhs_col_ptrs, &b));
+        BSM_TRY(dense_alloc(dtype, rows, rhs_cols, &c));
+        BSM_TRY(bsm_spmm(a, b, c, algo));
+        BSM_TRY(dense_to_csr_impl(c, &r));
+        hv = (T *)malloc(std::max<uint64_t>(1, r->nnz) * sizeof(T));
+        hc = (uint64_t *)malloc(std::max<uint64_t>(1, r->nnz) * 8);
+        hr = (uint64_t *)malloc((r->rows + 1) * 8);
+        if (!hv || !hc || !hr) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense_host: out of host memory");
+        BSM_TRY((csr_download<T>(r, dtype, hv, hc, hr)));
+        *out_nnz = r->nnz;
+        return BSM_OK;
+    }();
+    if (a) bsm_csr_free(a);
+    if (b) bsm_dense_free(b);
+    if (c) bsm_dense_free(c);
+    if (r) bsm_csr_free(r);
+    if (st != BSM_OK) {
+        free(hv);
+        free(hc);
+        free(hr);
+        return st;
+    }
+    *out_v = hv;
+    *out_col_index = hc;
+    *out_row_index = hr;
+    return BSM_OK;
+}
+
+template <typename T>
+static int mul_vector(const bsm_csr *a, int dtype, const T *rhs, uint64_t rhs_len, T *out, uint64_t out_len)
+{
+    BSM_TRY(ensure_init());
+    if (!a) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_vector: null handle");
+    if (a->dtype != dtype) return fail(BSM_ERR_DTYPE_MISMATCH, "mul_vector: dtype mismatch");
+    // src/sparse.rs:469-471
+    if (a->cols != rhs_len || a->rows != out_len)
+        return fail(BSM_ERR_INCORRECT_DIMENSIONS, "mul_vector: dims (MatErr::IncorrectDimensions)");
+    bsm_dense *x = nullptr, *y = nullptr;
+    int st = [&]() -> int {
+        BSM_TRY(dense_alloc(dtype, rhs_len, 1, &x));
+        BSM_TRY(dense_alloc(dtype, out_len, 1, &y));
+        if (rhs_len) BSM_CUDA(cudaMemcpyAsync(x->data, rhs, rhs_len * sizeof(T), cudaMemcpyHostToDevice, g_rt.stream));
+        BSM_TRY(bsm_spmm(a, x, y, BSM_ALGO_AUTO));
+        if (out_len) BSM_CUDA(cudaMemcpyAsync(out, y->data, out_len * sizeof(T), cudaMemcpyDeviceToHost, g_rt.stream));
+        BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
+        return BSM_OK;
+    }();
+    if (x) bsm_dense_free(x);
+    if (y) bsm_dense_free(y);
+    return st;
+}
+
+template <typename CountFn, typename FillFn>
+static int gen_counted(int dtype, uint64_t rows, uint64_t cols, CountFn count_fn, FillFn fill_fn, bsm_csr **out)
+{
+    BSM_TRY(ensure_init());
+    if (!out) return fail(BSM_ERR_INVALID_ARGUMENT, "gen: null out");
+    if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "gen: dtype must be f32 or f64");
+    if (rows >= 0xFFFFFFF0ull) return fail(BSM_ERR_INDEX_OVERFLOW, "gen: too many rows");
+    cudaStream_t sm = g_rt.stream;
+    uint32_t *counts = nullptr;
+    bsm_csr *a = nullptr;
+    int st = [&]() -> int {
+        BSM_CUDA(cudaMalloc(&counts, (rows + 1) * 4 + 16));
+        BSM_CUDA(cudaMemsetAsync(counts, 0, (rows + 1) * 4 + 16, sm));
+        BSM_TRY(count_fn(counts, sm));
+        BSM_TRY(exclusive_scan_u32(counts, counts, rows + 1, sm));
+        uint32_t nnz = 0;
+        BSM_CUDA(cudaMemcpyAsync(&nnz, counts + rows, 4, cudaMemcpyDeviceToHost, sm));
+        BSM_CUDA(cudaStreamSynchronize(sm));
+        BSM_TRY(alloc_csr(dtype, rows, cols, nnz, &a));
+        BSM_CUDA(cudaMemcpyAsync(a->row_ptr, counts, (rows + 1) * 4, cudaMemcpyDeviceToDevice, sm));
+        BSM_TRY(fill_fn(a, sm));
+        return compute_stats(a);
+    }();
+    if (counts) cudaFree(counts);
+    if (st != BSM_OK) {
+        if (a) bsm_csr_free(a);
+        return st;
+    }
+    *out = a;
+    return BSM_OK;
+}
+
+}  // namespace bsm
+
+using namespace bsm;
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+extern "C" {
+
+int bsm_abi_version(void) { return BSM_ABI_VERSION; }
+
+int bsm_device_count(int *count)
+{
+    if (!count) return fail(BSM_ERR_INVALID_ARGUMENT, "device_count: null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(BSM_ERR_NO_DEVICE, std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return BSM_OK;
+}
+
+int bsm_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(BSM_ERR_NO_DEVICE, std::string("no usable CUDA device (this library has no CPU fallback): ") +
+                                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(BSM_ERR_INVALID_ARGUMENT, "bsm_init: device index out of range");
+    BSM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BSM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (g_rt.own_stream && g_rt.device != device) {
+        cudaStreamDestroy(g_rt.own_stream);
+        g_rt.own_stream = nullptr;
+    }
+    if (!g_rt.own_stream) BSM_CUDA(cudaStreamCreateWithFlags(&g_rt.own_stream, cudaStreamNonBlocking));
+    g_rt.stream = g_rt.own_stream;
+    g_rt.device = device;
+    g_rt.sm_count = prop.multiProcessorCount;
+    g_rt.l2_bytes = (size_t)prop.l2CacheSize;
+    g_rt.hbm_bytes = prop.totalGlobalMem;
+    g_rt.cc_major = prop.major;
+    g_rt.cc_minor = prop.minor;
+    g_rt.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    return BSM_OK;
+}
+
+int bsm_set_stream(void *cuda_stream)
+{
+    BSM_TRY(ensure_init());
+    g_rt.stream = cuda_stream ? (cudaStream_t)cuda_stream : g_rt.own_stream;
+    return BSM_OK;
+}
+
+int bsm_sync(void)
+{
+    BSM_TRY(ensure_init());
+    BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
+    return BSM_OK;
+}
+
+const char *bsm_last_error_string(void) { return g_err.c_str(); }
+
+const char *bsm_status_string(int status)
+{
+    switch (status) {
+        case BSM_OK: return "ok";
+        case BSM_ERR_INCORRECT_DIMENSIONS: return "IncorrectDimensions";
+        case BSM_ERR_NOT_FINALISED: return "MatrixNotFinalised";
+        case BSM_ERR_OUT_OF_BOUNDS: return "OutOfBounds";
+        case BSM_ERR_INDEX_OVERFLOW: return "IndexOverflow";
+        case BSM_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+        case BSM_ERR_DTYPE_MISMATCH: return "DtypeMismatch";
+        case BSM_ERR_CUDA: return "CudaError";
+        case BSM_ERR_NCCL: return "NcclError";
+        case BSM_ERR_NO_DEVICE: return "NoDevice";
+        case BSM_ERR_NOT_SUPPORTED: return "NotSupported";
+    }
+    return "unknown";
+}
+
+int bsm_device_info(int *sm_count, size_t *l2_bytes, size_t *hbm_bytes, int *cc_major, int *cc_minor)
+{
+    BSM_TRY(ensure_init());
+    if (sm_count) *sm_count = g_rt.sm_count;
+    if (l2_bytes) *l2_bytes = g_rt.l2_bytes;
+    if (hbm_bytes) *hbm_bytes = g_rt.hbm_bytes;
+    if (cc_major) *cc_major = g_rt.cc_major;
+    if (cc_minor) *cc_minor = g_rt.cc_minor;
+    return BSM_OK;
+}
+
+// ---- Csr --------------------------------------------------------------------------------------
+int bsm_csr_upload_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v, const uint64_t *col_index,
+                       const uint64_t *row_index, uint64_t row_index_len, bsm_csr **out)
+{
+    return csr_upload<double>(BSM_F64, rows, cols, nnz, v, col_index, row_index, row_index_len, out);
+}
+int bsm_csr_upload_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const float *v, const uint64_t *col_index,
+                       const uint64_t *row_index, uint64_t row_index_len, bsm_csr **out)
+{
+    return csr_upload<float>(BSM_F32, rows, cols, nnz, v, col_index, row_index, row_index_len, out);
+}
+int bsm_csr_upload_rows_f64(uint64_t rows, uint64_t cols, const double *v, const uint64_t *col_index,
+                            const uint64_t *row_index, uint64_t row_begin, uint64_t row_end, bsm_csr **out)
+{
+    return csr_upload_rows<double>(BSM_F64, rows, cols, v, col_index, row_index, row_begin, row_end, out);
+}
+int bsm_csr_upload_rows_f32(uint64_t rows, uint64_t cols, const float *v, const uint64_t *col_index,
+                            const uint64_t *row_index, uint64_t row_begin, uint64_t row_end, bsm_csr **out)
+{
+    return csr_upload_rows<float>(BSM_F32, rows, cols, v, col_index, row_index, row_begin, row_end, out);
+}
+
+int bsm_csr_from_device(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const void *d_vals, const uint32_t *d_col_idx,
+                        const uint32_t *d_row_ptr, int copy, bsm_csr **out)
+{
+    BSM_TRY(ensure_init());
+    if (!out || !d_row_ptr || (nnz && (!d_vals || !d_col_idx))) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_from_device: null argument");
+    if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "csr_from_device: dtype must be f32 or f64");
+    bsm_csr *a = nullptr;
+    if (copy) {
+        BSM_TRY(alloc_csr(dtype, rows, cols, nnz, &a));
+        cudaStream_t sm = g_rt.stream;
+        cudaMemcpyAsync(a->vals, d_vals, nnz * dtype_size(dtype), cudaMemcpyDeviceToDevice, sm);
+        cudaMemcpyAsync(a->col_idx, d_col_idx, nnz * 4, cudaMemcpyDeviceToDevice, sm);
+        cudaMemcpyAsync(a->row_ptr, d_row_ptr, (rows + 1) * 4, cudaMemcpyDeviceToDevice, sm);
+    } else {
+        if (rows >= 0xFFFFFFF0ull || cols >= 0xFFFFFFF0ull || nnz >= 0xFFFFFFF0ull)
+            return fail(BSM_ERR_INDEX_OVERFLOW, "rows, cols and nnz must fit the device's u32 indices");
+        if (((uintptr_t)d_vals | (uintptr_t)d_col_idx | (uintptr_t)d_row_ptr) & 15)
+            return fail(BSM_ERR_INVALID_ARGUMENT, "csr_from_device: borrowed arrays must be 16-byte aligned");
+        a = new bsm_csr();
+        a->dtype = dtype;
+        a->rows = rows;
+        a->cols = cols;
+        a->nnz = nnz;
+        a->vals = const_cast<void *>(d_vals);
+        a->col_idx = const_cast<uint32_t *>(d_col_idx);
+        a->row_ptr = const_cast<uint32_t *>(d_row_ptr);
+        a->owns = false;
+    }
+    int st = compute_stats(a);
+    if (st != BSM_OK) {
+        bsm_csr_free(a);
+        return st;
+    }
+    *out = a;
+    return BSM_OK;
+}
+
+int bsm_csr_free(bsm_csr *a)
+{
+    if (!a) return BSM_OK;
+    if (a->owns) {
+        if (a->vals) cudaFree(a->vals);
+        if (a->col_idx) cudaFree(a->col_idx);
+        if (a->row_ptr) cudaFree(a->row_ptr);
+    }
+    if (a->part_rows) cudaFree(a->part_rows);
+    if (a->carry_vals) cudaFree(a->carry_vals);
+    if (a->carry_rows) cudaFree(a->carry_rows);
+    delete a;
+    return BSM_OK;
+}
+
+int bsm_csr_info(const bsm_csr *a, int *dtype, uint64_t *rows, uint64_t *cols, uint64_t *nnz, uint64_t *max_row_nnz)
+{
+    if (!a) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_info: null handle");
+    if (dtype) *dtype = a->dtype;
+    if (rows) *rows = a->rows;
+    if (cols) *cols = a->cols;
+    if (nnz) *nnz = a->nnz;
+    if (max_row_nnz) *max_row_nnz = a->max_row_nnz;
+    return BSM_OK;
+}
+
+int bsm_csr_device_ptrs(const bsm_csr *a, const void **d_vals, const uint32_t **d_col_idx, const uint32_t **d_row_ptr)
+{
+    if (!a) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_device_ptrs: null handle");
+    if (d_vals) *d_vals = a->vals;
+    if (d_col_idx) *d_col_idx = a->col_idx;
+    if (d_row_ptr) *d_row_ptr = a->row_ptr;
+    return BSM_OK;
+}
+
+int bsm_csr_download_f64(const bsm_csr *a, double *v, uint64_t *col_index, uint64_t *row_index)
+{
+    return csr_download<double>(a, BSM_F64, v, col_index, row_index);
+}
+int bsm_csr_download_f32(const bsm_csr *a, float *v, uint64_t *col_index, uint64_t *row_index)
+{
+    return csr_download<float>(a, BSM_F32, v, col_index, row_index);
+}
+
+// ---- Dense ------------------------------------------------------------------------------------
+int bsm_dense_upload_f64(uint64_t rows, uint64_t cols, const double *const *col_ptrs, bsm_dense **out)
+{
+    return dense_upload<double>(BSM_F64, rows, cols, col_ptrs, out);
+}
+int bsm_dense_upload_f32(uint64_t rows, uint64_t cols, const float *const *col_ptrs, bsm_dense **out)
+{
+    return dense_upload<float>(BSM_F32, rows, cols, col_ptrs, out);
+}
+int bsm_dense_alloc(int dtype, uint64_t rows, uint64_t cols, bsm_dense **out) { return dense_alloc(dtype, rows, cols, out); }
+
+int bsm_dense_borrow(int dtype, uint64_t rows, uint64_t cols, void *d_rowmajor, uint64_t ld, bsm_dense **out)
+{
+    BSM_TRY(ensure_init());
+    if (!out || (!d_rowmajor && rows && cols) || ld < cols) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_borrow: bad arguments");
+    if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "dense_borrow: dtype must be f32 or f64");
+    bsm_dense *d = new bsm_dense();
+    d->dtype = dtype;
+    d->rows = rows;
+    d->cols = cols;
+    d->ld = ld ? ld : 1;
+    d->data = d_rowmajor;
+    d->owns = false;
+    *out = d;
+    return BSM_OK;
+}
+
+int bsm_dense_free(bsm_dense *d)
+{
+    if (!d) return BSM_OK;
+    if (d->owns && d->data) cudaFree(d->data);
+    delete d;
+    return BSM_OK;
+}
+
+int bsm_dense_info(const bsm_dense *d, int *dtype, uint64_t *rows, uint64_t *cols, uint64_t *ld, void **d_ptr)
+{
+    if (!d) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_info: null handle");
+    if (dtype) *dtype = d->dtype;
+    if (rows) *rows = d->rows;
+    if (cols) *cols = d->cols;
+    if (ld) *ld = d->ld;
+    if (d_ptr) *d_ptr = d->data;
+    return BSM_OK;
+}
+
+int bsm_dense_download_f64(const bsm_dense *d, double *const *col_ptrs) { return dense_download<double>(d, BSM_F64, col_ptrs); }
+int bsm_dense_download_f32(const bsm_dense *d, float *const *col_ptrs) { return dense_download<float>(d, BSM_F32, col_ptrs); }
+
+int bsm_dense_download_rowmajor(const bsm_dense *d, void *dst)
+{
+    BSM_TRY(ensure_init());
+    if (!d || (!dst && d->rows && d->cols)) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_download_rowmajor: null argument");
+    if (d->rows == 0 || d->cols == 0) return BSM_OK;
+    const size_t s = dtype_size(d->dtype);
+    BSM_CUDA(cudaMemcpy2DAsync(dst, d->cols * s, d->data, d->ld * s, d->cols * s, d->rows, cudaMemcpyDeviceToHost, g_rt.stream));
+    BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
+    return BSM_OK;
+}
+
+int bsm_dense_upload_rowmajor(int dtype, uint64_t rows, uint64_t cols, const void *src, bsm_dense **out)
+{
+    bsm_dense *d = nullptr;
+    BSM_TRY(dense_alloc(dtype, rows, cols, &d));
+    if (rows && cols) {
+        if (!src) {
+            bsm_dense_free(d);
+            return fail(BSM_ERR_INVALID_ARGUMENT, "dense_upload_rowmajor: null src");
+        }
+        const size_t s = dtype_size(dtype);
+        cudaError_t e = cudaMemcpy2DAsync(d->data, d->ld * s, src, cols * s, cols * s, rows, cudaMemcpyHostToDevice, g_rt.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_rt.stream);
+        if (e != cudaSuccess) {
+            bsm_dense_free(d);
+            return fail(BSM_ERR_CUDA, std::string("dense_upload_rowmajor: ") + cudaGetErrorString(e));
+        }
+    }
+    *out = d;
+    return BSM_OK;
+}
+
+// ---- hot path ------------------------------------------------------------------------------------
+int bsm_spmm(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, int algo)
+{
+    bsm_tuning tn{};
+    tn.algo = algo;
+    return spmm_dispatch(a, b, c, &tn);
+}
+int bsm_spmm_tuned(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning *tuning)
+{
+    return spmm_dispatch(a, b, c, tuning);
+}
+int bsm_last_launch_info(bsm_launch_info *info)
+{
+    if (!info) return fail(BSM_ERR_INVALID_ARGUMENT, "last_launch_info: null");
+    *info = g_info;
+    return BSM_OK;
+}
+uint64_t bsm_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int bsm_dense_to_csr(const bsm_dense *d, bsm_csr **out) { return dense_to_csr_impl(d, out); }
+
+int bsm_mul_dense_host_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v, const uint64_t *col_index,
+                           const uint64_t *row_index, uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                           const double *const *rhs_col_ptrs, int algo, uint64_t *out_nnz, double **out_v,
+                           uint64_t **out_col_index, uint64_t **out_row_index)
+{
+    return mul_dense_host<double>(BSM_F64, rows, cols, nnz, v, col_index, row_index, row_index_len, rhs_rows, rhs_cols,
+                                  rhs_col_ptrs, algo, out_nnz, out_v, out_col_index, out_row_index);
+}
+int bsm_mul_dense_host_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const float *v, const uint64_t *col_index,
+                           const uint64_t *row_index, uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                           const float *const *rhs_col_ptrs, int algo, uint64_t *out_nnz, float **out_v,
+                           uint64_t **out_col_index, uint64_t **out_row_index)
+{
+    return mul_dense_host<float>(BSM_F32, rows, cols, nnz, v, col_index, row_index, row_index_len, rhs_rows, rhs_cols,
+                                 rhs_col_ptrs, algo, out_nnz, out_v, out_col_index, out_row_index);
+}
+void bsm_host_free(void *p) { free(p); }
+
+int bsm_mul_vector_f64(const bsm_csr *a, const double *rhs, uint64_t rhs_len, double *out, uint64_t out_len)
+{
+    return mul_vector<double>(a, BSM_F64, rhs, rhs_len, out, out_len);
+}
+int bsm_mul_vector_f32(const bsm_csr *a, const float *rhs, uint64_t rhs_len, float *out, uint64_t out_len)
+{
+    return mul_vector<float>(a, BSM_F32, rhs, rhs_len, out, out_len);
+}
+
+// ---- sharding ------------------------------------------------------------------------------------
+int bsm_partition_rows(const uint64_t *row_index, uint64_t rows, int parts, uint64_t *bounds)
+{
+    if (!row_index || !bounds || parts < 1) return fail(BSM_ERR_INVALID_ARGUMENT, "partition_rows: bad arguments");
+    const uint64_t nnz = row_index[rows] - row_index[0];
+    bounds[0] = 0;
+    for (int p = 1; p < parts; ++p) {
+        // first row whose start offset reaches p/parts of the entries (ties -> equal row counts)
+        const uint64_t target = row_index[0] + (uint64_t)((__uint128_t)nnz * (unsigned)p / (unsigned)parts);
+        uint64_t r;
+        if (nnz == 0) {
+            r = rows * (uint64_t)p / (uint64_t)parts;
+        } else {
+            r = (uint64_t)(std::lower_bound(row_index, row_index + rows + 1, target) - row_index);
+            if (r > rows) r = rows;
+        }
+        bounds[p] = std::max(r, bounds[p - 1]);
+    }
+    bounds[parts] = rows;
+    return BSM_OK;
+}
+
+// ---- generators ------------------------------------------------------------------------------------
+int bsm_gen_dense(int dtype, uint64_t rows, uint64_t cols, uint64_t seed, int mode, double offset, bsm_dense **out)
+{
+    bsm_dense *d = nullptr;
+    BSM_TRY(dense_alloc(dtype, rows, cols, &d));
+    int st = launch_gen_dense(dtype, d->data, rows, cols, d->ld, seed, mode, offset, g_rt.stream);
+    if (st != BSM_OK) {
+        bsm_dense_free(d);
+        return st;
+    }
+    *out = d;
+    return BSM_OK;
+}
+
+int bsm_gen_laplacian(int dtype, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t row_begin, uint64_t row_end, bsm_csr **out)
+{
+    if (nx == 0 || ny == 0 || nz == 0) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_laplacian: empty grid");
+    const uint64_t n = nx * ny * nz;
+    if (row_begin > row_end || row_end > n) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_laplacian: bad row range");
+    return gen_counted(
+        dtype, row_end - row_begin, n,
+        [&](uint32_t *counts, cudaStream_t sm) { return launch_laplacian_counts(nx, ny, nz, row_begin, row_end, counts, sm); },
+        [&](bsm_csr *a, cudaStream_t sm) {
+            return launch_laplacian_fill(dtype, nx, ny, nz, row_begin, row_end, a->row_ptr, a->col_idx, a->vals, sm);
+        },
+        out);
+}
+
+int bsm_gen_band(int dtype, uint64_t n, uint64_t hb, uint64_t row_begin, uint64_t row_end, bsm_csr **out)
+{
+    if (n == 0 || row_begin > row_end || row_end > n) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_band: bad arguments");
+    return gen_counted(
+        dtype, row_end - row_begin, n,
+        [&](uint32_t *counts, cudaStream_t sm) { return launch_band_counts(n, hb, row_begin, row_end, counts, sm); },
+        [&](bsm_csr *a, cudaStream_t sm) {
+            return launch_band_fill(dtype, n, hb, row_begin, row_end, a->row_ptr, a->col_idx, a->vals, sm);
+        },
+        out);
+}
+
+int bsm_gen_rmat(int dtype, int scale, uint64_t edges, double pa, double pb, double pc, uint64_t seed, int mode, bsm_csr **out)
+{
+    BSM_TRY(ensure_init());
+    if (!out) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_rmat: null out");
+    if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "gen_rmat: dtype must be f32 or f64");
+    if (scale < 1 || scale > 31) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_rmat: scale must be in [1,31]");
+    const uint64_t rows = 1ull << scale;
+    bsm_csr *a = nullptr;
+    BSM_TRY(alloc_csr(dtype, rows, rows, edges, &a));
+    int st = gen_rmat_device(dtype, scale, edges, pa, pb, pc, seed, mode, a->row_ptr, a->col_idx, a->vals, g_rt.stream);
+    if (st == BSM_OK) st = compute_stats(a);
+    if (st != BSM_OK) {
+        bsm_csr_free(a);
+        return st;
+    }
+    *out = a;
+    return BSM_OK;
+}
+
+int bsm_l2_flush(void)
+{
+    BSM_TRY(ensure_init());
+    const size_t want = std::max<size_t>(g_rt.l2_bytes * 2, (size_t)256 << 20);
+    if (g_rt.flush_bytes < want) {
+        if (g_rt.flush_buf) cudaFree(g_rt.flush_buf);
+        g_rt.flush_buf = nullptr;
+        g_rt.flush_bytes = 0;
+        BSM_CUDA(cudaMalloc(&g_rt.flush_buf, want));
+        g_rt.flush_bytes = want;
+    }
+    BSM_CUDA(cudaMemsetAsync(g_rt.flush_buf, 0, g_rt.flush_bytes, g_rt.stream));
+    return BSM_OK;
+}
+
+}  // extern "C"

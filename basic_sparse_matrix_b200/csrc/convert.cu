@@ -1,0 +1,319 @@
+// convert.cu — format conversion on either side of the hot path (sm_100a):
+//   * usize (u64) -> u32 index narrowing with bound check   (Csr fields, src/sparse.rs:72-73)
+//   * column-major Vec<Vec<T>> <-> row-major device Dense    (src/dense.rs:5-9)
+//   * csr_row_stats (max row length -> kernel dispatch)
+//   * dense -> Csr zero-drop compaction: count -> scan -> scatter
+//     (result construction of mul_dense: sparse.rs:442 -> insert 222-233 -> finalise 206-219)
+#include "bsm_common.cuh"
+#include "kernels.h"
+
+namespace bsm {
+
+// ---- index narrowing / widening --------------------------------------------------------------
+__global__ void narrow_u64_kernel(const uint64_t *__restrict__ src, uint32_t *__restrict__ dst, uint64_t count,
+                                  uint64_t bound, uint64_t subtract, uint32_t *flag)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint64_t v = src[i] - subtract;
+        bad |= v >= bound;
+        dst[i] = (uint32_t)v;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 1u);
+}
+
+__global__ void widen_u32_kernel(const uint32_t *__restrict__ src, uint64_t *__restrict__ dst, uint64_t count)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = src[i];
+}
+
+__global__ void fill_u32_kernel(uint32_t *dst, uint64_t count, uint32_t value)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = value;
+}
+
+static inline int grid_for(uint64_t count, int threads, int max_blocks = 148 * 16)
+{
+    uint64_t b = (count + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > (uint64_t)max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+int launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t count, uint64_t bound, uint64_t subtract,
+                      uint32_t *flag, cudaStream_t stream)
+{
+    if (count == 0) return BSM_OK;
+    narrow_u64_kernel<<<grid_for(count, 256), 256, 0, stream>>>(src, dst, count, bound, subtract, flag);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+int launch_widen_u32(const uint32_t *src, uint64_t *dst, uint64_t count, cudaStream_t stream)
+{
+    if (count == 0) return BSM_OK;
+    widen_u32_kernel<<<grid_for(count, 256), 256, 0, stream>>>(src, dst, count);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+int launch_fill_u32(uint32_t *dst, uint64_t count, uint32_t value, cudaStream_t stream)
+{
+    if (count == 0) return BSM_OK;
+    fill_u32_kernel<<<grid_for(count, 256), 256, 0, stream>>>(dst, count, value);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+// ---- csr_row_stats ---------------------------------------------------------------------------
+__global__ void row_stats_kernel(const uint32_t *__restrict__ row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t m = 0;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += stride) {
+        const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
+        if (b < a)
+            bad = true;
+        else
+            m = max(m, b - a);
+    }
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_len, m);
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicExch(bad_flag, 1u);
+}
+
+int launch_row_stats(const uint32_t *row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag, cudaStream_t stream)
+{
+    if (rows == 0) return BSM_OK;
+    row_stats_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(row_ptr, rows, max_len, bad_flag);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+// ---- layout transposes ---------------------------------------------------------------------------
+// colmajor[c*rows + r]  <->  rowmajor[r*ld + c]; 32x32 tiles through padded shared memory so both
+// sides are coalesced.
+template <typename T, bool TO_ROWMAJOR>
+__global__ void transpose_kernel(const T *__restrict__ src, T *__restrict__ dst, uint64_t rows, uint64_t cols, uint64_t ld)
+{
+    __shared__ T tile[32][33];
+    const uint64_t tiles_c = (cols + 31) / 32;
+    const uint64_t tiles_r = (rows + 31) / 32;
+    const uint64_t ntiles = tiles_c * tiles_r;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+        if (TO_ROWMAJOR) {
+            // read column-major: threadIdx.x walks rows (contiguous in a column)
+            for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+                const uint64_t c = c0 + j, r = r0 + threadIdx.x;
+                if (c < cols && r < rows) tile[j][threadIdx.x] = src[c * rows + r];
+            }
+            __syncthreads();
+            for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+                const uint64_t r = r0 + j, c = c0 + threadIdx.x;
+                if (c < cols && r < rows) dst[r * ld + c] = tile[threadIdx.x][j];
+            }
+        } else {
+            for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+                const uint64_t r = r0 + j, c = c0 + threadIdx.x;
+                if (c < cols && r < rows) tile[j][threadIdx.x] = src[r * ld + c];
+            }
+            __syncthreads();
+            for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+                const uint64_t c = c0 + j, r = r0 + threadIdx.x;
+                if (c < cols && r < rows) dst[c * rows + r] = tile[threadIdx.x][j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool TO_ROWMAJOR>
+static int launch_transpose(int dtype, const void *src, void *dst, uint64_t rows, uint64_t cols, uint64_t ld,
+                            cudaStream_t stream)
+{
+    if (rows == 0 || cols == 0) return BSM_OK;
+    const uint64_t ntiles = ((cols + 31) / 32) * ((rows + 31) / 32);
+    const int grid = (int)(ntiles < 148ull * 32 ? ntiles : 148ull * 32);
+    dim3 block(32, 8);
+    if (dtype == BSM_F64)
+        transpose_kernel<double, TO_ROWMAJOR><<<grid, block, 0, stream>>>((const double *)src, (double *)dst, rows, cols, ld);
+    else
+        transpose_kernel<float, TO_ROWMAJOR><<<grid, block, 0, stream>>>((const float *)src, (float *)dst, rows, cols, ld);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+int launch_transpose_cm2rm(int dtype, const void *colmajor, void *rowmajor, uint64_t rows, uint64_t cols, uint64_t ld,
+                           cudaStream_t stream)
+{
+    return launch_transpose<true>(dtype, colmajor, rowmajor, rows, cols, ld, stream);
+}
+int launch_transpose_rm2cm(int dtype, const void *rowmajor, void *colmajor, uint64_t rows, uint64_t cols, uint64_t ld,
+                           cudaStream_t stream)
+{
+    return launch_transpose<false>(dtype, rowmajor, colmajor, rows, cols, ld, stream);
+}
+
+// ---- exclusive scan (u32), three-phase, recursive over block sums -------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;   // 2048
+
+__global__ void scan_tile_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint64_t count,
+                                 uint32_t *__restrict__ tile_sums)
+{
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+    uint32_t v[kScanPerThread];
+    uint32_t local = 0;
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+        v[i] = base + i < count ? in[base + i] : 0u;
+        local += v[i];
+    }
+    // exclusive scan of `local` across the block
+    uint32_t incl = local;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (uint32_t)o) incl += n;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < kScanThreads / 32 ? warp_sums[lane] : 0u;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= (uint32_t)o) w += n;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t run = incl - local + (warp ? warp_sums[warp - 1] : 0u);
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i) {
+        if (base + i < count) out[base + i] = run;
+        run += v[i];
+    }
+    if (threadIdx.x == kScanThreads - 1 && tile_sums) tile_sums[blockIdx.x] = run;
+}
+
+__global__ void scan_add_kernel(uint32_t *__restrict__ out, uint64_t count, const uint32_t *__restrict__ tile_offsets)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+    const uint32_t off = tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kScanPerThread; ++i)
+        if (base + i < count) out[base + i] += off;
+}
+
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t count, cudaStream_t stream)
+{
+    if (count == 0) return BSM_OK;
+    const uint64_t tiles = (count + kScanTile - 1) / kScanTile;
+    uint32_t *tile_sums = nullptr;
+    if (tiles > 1) BSM_CUDA(cudaMallocAsync(&tile_sums, tiles * sizeof(uint32_t), stream));
+    scan_tile_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(in, out, count, tile_sums);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    if (tiles > 1) {
+        BSM_TRY(exclusive_scan_u32(tile_sums, tile_sums, tiles, stream));
+        scan_add_kernel<<<(unsigned)tiles, kScanThreads, 0, stream>>>(out, count, tile_sums);
+        BSM_CUDA(cudaGetLastError());
+        count_launch();
+        BSM_CUDA(cudaFreeAsync(tile_sums, stream));
+    }
+    return BSM_OK;
+}
+
+// ---- dense -> Csr zero-drop compaction ------------------------------------------------------------
+// keep(x) == (x != T::default()): NaN kept, -0.0 dropped (src/sparse.rs:229)
+template <typename T> __device__ __forceinline__ bool keep(T x) { return x != T(0); }
+
+// one warp per row
+template <typename T>
+__global__ void count_nonzero_kernel(const T *__restrict__ d, uint64_t rows, uint64_t cols, uint64_t ld,
+                                     uint32_t *__restrict__ counts, unsigned long long *total)
+{
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned long long local = 0;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        uint32_t n = 0;
+        for (uint64_t c0 = 0; c0 < cols; c0 += 32) {
+            const uint64_t c = c0 + lane;
+            const bool k = c < cols && keep(d[r * ld + c]);
+            n += __popc(__ballot_sync(0xFFFFFFFFu, k));
+        }
+        if (lane == 0) {
+            counts[r] = n;
+            local += n;
+        }
+    }
+    if (lane == 0 && local) atomicAdd(total, local);
+}
+
+template <typename T>
+__global__ void scatter_nonzero_kernel(const T *__restrict__ d, uint64_t rows, uint64_t cols, uint64_t ld,
+                                       const uint32_t *__restrict__ row_ptr, T *__restrict__ vals,
+                                       uint32_t *__restrict__ col_idx)
+{
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        uint32_t pos = row_ptr[r];
+        for (uint64_t c0 = 0; c0 < cols; c0 += 32) {
+            const uint64_t c = c0 + lane;
+            T x = T(0);
+            if (c < cols) x = d[r * ld + c];
+            const bool k = c < cols && keep(x);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, k);
+            if (k) {
+                const uint32_t o = pos + __popc(m & ((1u << lane) - 1u));   // ascending column = insertion order
+                vals[o] = x;
+                col_idx[o] = (uint32_t)c;
+            }
+            pos += __popc(m);
+        }
+    }
+}
+
+int launch_count_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t *counts,
+                         unsigned long long *total, cudaStream_t stream)
+{
+    if (rows == 0) return BSM_OK;
+    const int grid = grid_for(rows * 32, 256);
+    if (dtype == BSM_F64)
+        count_nonzero_kernel<double><<<grid, 256, 0, stream>>>((const double *)dense, rows, cols, ld, counts, total);
+    else
+        count_nonzero_kernel<float><<<grid, 256, 0, stream>>>((const float *)dense, rows, cols, ld, counts, total);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+int launch_scatter_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, const uint32_t *row_ptr,
+                           void *vals, uint32_t *col_idx, cudaStream_t stream)
+{
+    if (rows == 0) return BSM_OK;
+    const int grid = grid_for(rows * 32, 256);
+    if (dtype == BSM_F64)
+        scatter_nonzero_kernel<double><<<grid, 256, 0, stream>>>((const double *)dense, rows, cols, ld, row_ptr, (double *)vals, col_idx);
+    else
+        scatter_nonzero_kernel<float><<<grid, 256, 0, stream>>>((const float *)dense, rows, cols, ld, row_ptr, (float *)vals, col_idx);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+}  // namespace bsm

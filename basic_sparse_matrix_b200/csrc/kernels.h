@@ -1,0 +1,91 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (internal interface).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bsm {
+
+// How one output row is spread over a warp: each lane owns V consecutive columns per register
+// tile, G lanes form the group that owns a row, NT register tiles per lane.
+// One pass covers G*V*NT columns.
+struct Shape {
+    int V = 1, G = 1, NT = 1;
+};
+
+// ---- vector-CSR ("row") kernel -----------------------------------------------------------
+struct RowParams {
+    const uint32_t *row_ptr;
+    const uint32_t *col_idx;
+    const void *vals;
+    const void *B;   // already offset to the first column of this pass
+    void *C;         // likewise
+    uint32_t rows;
+    uint32_t n;      // columns in this pass
+    uint32_t ldb, ldc;
+    uint32_t rb;     // rows per batch (multiple of 4)
+    uint32_t num_batches;
+    uint32_t cap;    // staged entries per stage (multiple of 4)
+    uint32_t stages;
+    uint32_t rows_per_warp;  // rows of a batch owned by one compute warp
+    uint32_t far_thr;        // 0 = off
+    uint32_t flags;          // BSM_TUNE_*
+};
+size_t row_kernel_smem_bytes(int dtype, const RowParams &p);
+int row_kernel_occupancy(int dtype, Shape sh, int block, size_t smem, int *blocks_per_sm);
+int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int grid, int block, size_t smem,
+                     cudaStream_t stream);
+
+// ---- merge-path kernel ---------------------------------------------------------------------
+struct MergeParams {
+    const uint32_t *row_ptr;
+    const uint32_t *col_idx;
+    const void *vals;
+    const void *B;
+    void *C;
+    const uint32_t *part_rows;  // [num_chunks+1]
+    void *carry_vals;           // [num_chunks][ldcar]
+    uint32_t *carry_rows;       // [num_chunks]
+    uint32_t rows, nnz;
+    uint32_t n, ldb, ldc, ldcar;
+    uint32_t items;             // merge items (rows + nnz) per lane group
+    uint32_t num_chunks;
+    uint32_t flags;
+};
+size_t merge_kernel_smem_bytes(int dtype, Shape sh, int block, uint32_t items);
+int launch_merge_partition(const uint32_t *row_ptr, uint32_t rows, uint32_t nnz, uint32_t items,
+                           uint32_t num_chunks, uint32_t *part_rows, cudaStream_t stream);
+int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, cudaStream_t stream,
+                      int *grid_out);
+int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream);
+
+// ---- format conversion / construction (convert.cu) ---------------------------------------------
+int launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t count, uint64_t bound, uint64_t subtract,
+                      uint32_t *flag /* set to 1 when (v - subtract) >= bound */, cudaStream_t stream);
+int launch_row_stats(const uint32_t *row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag, cudaStream_t stream);
+int launch_transpose_cm2rm(int dtype, const void *colmajor, void *rowmajor, uint64_t rows, uint64_t cols, uint64_t ld,
+                           cudaStream_t stream);
+int launch_transpose_rm2cm(int dtype, const void *rowmajor, void *colmajor, uint64_t rows, uint64_t cols, uint64_t ld,
+                           cudaStream_t stream);
+int launch_widen_u32(const uint32_t *src, uint64_t *dst, uint64_t count, cudaStream_t stream);
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t count, cudaStream_t stream);  // out may alias in
+int launch_count_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t *counts,
+                         unsigned long long *total, cudaStream_t stream);
+int launch_scatter_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld,
+                           const uint32_t *row_ptr, void *vals, uint32_t *col_idx, cudaStream_t stream);
+int launch_fill_u32(uint32_t *dst, uint64_t count, uint32_t value, cudaStream_t stream);
+
+// ---- synthetic generators (gen.cu) -----------------------------------------------------------------
+int launch_gen_dense(int dtype, void *data, uint64_t rows, uint64_t cols, uint64_t ld, uint64_t seed, int mode,
+                     double offset, cudaStream_t stream);
+int launch_laplacian_counts(uint64_t nx, uint64_t ny, uint64_t nz, uint64_t row_begin, uint64_t row_end,
+                            uint32_t *counts, cudaStream_t stream);
+int launch_laplacian_fill(int dtype, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t row_begin, uint64_t row_end,
+                          const uint32_t *row_ptr, uint32_t *col_idx, void *vals, cudaStream_t stream);
+int launch_band_counts(uint64_t n, uint64_t hb, uint64_t row_begin, uint64_t row_end, uint32_t *counts,
+                       cudaStream_t stream);
+int launch_band_fill(int dtype, uint64_t n, uint64_t hb, uint64_t row_begin, uint64_t row_end, const uint32_t *row_ptr,
+                     uint32_t *col_idx, void *vals, cudaStream_t stream);
+int gen_rmat_device(int dtype, int scale, uint64_t edges, double a, double b, double c, uint64_t seed, int mode,
+                    uint32_t *row_ptr /* [2^scale+1] */, uint32_t *col_idx, void *vals, cudaStream_t stream);
+
+}  // namespace bsm

@@ -1,0 +1,287 @@
+// spmm_merge.cu — nnz-balanced merge-path SpMM/SpMV for power-law rows (sm_100a).
+//
+// Same contraction as Csr::mul_dense (/root/reference/src/sparse.rs:431-444), but the work is
+// split along the merge path of (row ends, entries) so every lane group gets exactly `items`
+// units of (rows closed + entries consumed), whatever the row-length distribution:
+//   * merge_partition_kernel: binary search of each chunk boundary's diagonal; depends only on A,
+//     computed once per matrix and cached in the handle;
+//   * spmm_merge_kernel: a CTA stages the contiguous col_idx/values slice (and the row_ptr slice)
+//     of its lane groups' chunks into shared memory with TMA bulk copies (cp.async.bulk), then
+//     every group walks its chunk in stored order: gathers B rows with coalesced vector loads,
+//     FMA-accumulates, and writes each row it closes exactly once. Entries that belong to a row
+//     closed by a later chunk leave the group as one carry-out (row, n partial sums);
+//   * merge_fixup_kernel: for every row with carry-outs, adds them in chunk order (deterministic,
+//     no atomics): C[row] = (carry_0 + carry_1 + ...) + tail.
+// Long rows are therefore summed as a few partial sums instead of one left-to-right chain —
+// within the stated tolerance of the reference (and exact for exactly representable data).
+#include "bsm_common.cuh"
+#include "kernels.h"
+
+namespace bsm {
+
+constexpr uint32_t kNoCarry = 0xFFFFFFFFu;
+
+// One thread per chunk boundary: first row the chunk closes (CUB-style merge-path search over
+// list A = row_end[i] = row_ptr[i+1] and list B = 0..nnz-1).
+__global__ void merge_partition_kernel(const uint32_t *__restrict__ row_ptr, uint32_t rows, uint32_t nnz, uint32_t items,
+                                       uint32_t num_chunks, uint32_t *__restrict__ part_rows)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > num_chunks) return;
+    const uint64_t total = (uint64_t)rows + nnz;
+    const uint64_t d64 = min((uint64_t)c * items, total);
+    const uint32_t d = (uint32_t)d64;
+    uint32_t lo = d > nnz ? d - nnz : 0u;
+    uint32_t hi = min(d, rows);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(row_ptr + mid + 1) <= d - mid - 1)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    part_rows[c] = lo;
+}
+
+template <typename T, int V, int G, int NT>
+__global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    constexpr int U = NT >= 4 ? 2 : (NT == 2 ? 4 : 8);
+    const uint32_t groups_per_cta = (blockDim.x / 32) * (32 / G);
+    const uint32_t span = groups_per_cta * p.items;   // merge items per CTA
+
+    // shared layout: vals[span+4] | idx[span+4] | rp[span+8]
+    T *val_s = reinterpret_cast<T *>(smem);
+    uint32_t *idx_s = reinterpret_cast<uint32_t *>(smem + (size_t)(span + 4) * sizeof(T));
+    uint32_t *rp_s = idx_s + (span + 4);
+
+    const uint32_t c0 = blockIdx.x * groups_per_cta;
+    const uint32_t cend = min(c0 + groups_per_cta, p.num_chunks);
+    const uint32_t total = p.rows + p.nnz;
+    const uint32_t R0 = __ldg(p.part_rows + c0);
+    const uint32_t R1 = __ldg(p.part_rows + cend);
+    const uint32_t Z0 = c0 * p.items - R0;
+    const uint32_t Z1 = min(cend * p.items, total) - R1;
+    const uint32_t z_a = Z0 & ~3u;                       // aligned first staged entry
+    const uint32_t rp_a = (R0 + 1u) & ~3u;               // aligned first staged row_ptr index
+    const uint32_t cnt = Z1 > Z0 ? ((Z1 - z_a + 3u) & ~3u) : 0u;
+    const uint32_t cnt_r = R1 > R0 ? ((R1 + 1u - rp_a + 3u) & ~3u) : 0u;   // rp[R0+1 .. R1]
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint64_t policy = (p.flags & BSM_TUNE_A_EVICT_FIRST) ? l2_policy_evict_first() : l2_policy_evict_normal();
+        mbar_arrive_expect_tx(&bar, cnt * (4u + (uint32_t)sizeof(T)) + cnt_r * 4u);
+        if (cnt) {
+            bulk_g2s(idx_s, p.col_idx + z_a, cnt * 4u, &bar, policy);
+            bulk_g2s(val_s, static_cast<const T *>(p.vals) + z_a, cnt * (uint32_t)sizeof(T), &bar, policy);
+        }
+        if (cnt_r) bulk_g2s(rp_s, p.row_ptr + rp_a, cnt_r * 4u, &bar, policy);
+    }
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t grp = (threadIdx.x >> 5) * (32 / G) + lane / G;
+    const uint32_t gl = lane % G;
+    const uint32_t c = c0 + grp;
+    const bool active = c < cend;
+
+    uint32_t row = 0, row_next = 0, nz = 0, nz_end = 0;
+    if (active) {
+        row = __ldg(p.part_rows + c);
+        row_next = __ldg(p.part_rows + c + 1);
+        nz = c * p.items - row;
+        nz_end = min((c + 1) * p.items, total) - row_next;
+    }
+    bool col_ok[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) col_ok[t] = (uint32_t)((t * G + gl) * V) < p.n;
+    const T *__restrict__ b_lane = static_cast<const T *>(p.B) + gl * V;
+    T *__restrict__ c_lane = static_cast<T *>(p.C) + gl * V;
+    const bool streaming = (p.flags & BSM_TUNE_C_STREAMING) != 0;
+
+    mbar_wait(&bar, 0);   // staged slices have landed
+    if (!active) return;
+
+    Lane<T, V> acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t].zero();
+    bool dirty = false;   // entries accumulated since the last row close
+    uint32_t row_end = row < row_next ? rp_s[row + 1 - rp_a] : kNoCarry;
+
+    auto close_row = [&]() {
+        T *crow = c_lane + (size_t)row * p.ldc;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            if (col_ok[t]) acc[t].store(crow + t * G * V, streaming);
+            acc[t].zero();
+        }
+        dirty = false;
+        ++row;
+        row_end = row < row_next ? rp_s[row + 1 - rp_a] : kNoCarry;
+    };
+
+    for (uint32_t e0 = nz; e0 < nz_end; e0 += U) {
+        Lane<T, V> b[U][NT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e0 + u < nz_end) {
+                const uint32_t col = idx_s[e0 + u - z_a];
+                const T *brow = b_lane + (size_t)col * p.ldb;
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+                    if (col_ok[t]) b[u][t].load(brow + t * G * V, false);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (e0 + u < nz_end) {
+                while (e0 + u >= row_end) close_row();   // rows (possibly empty) ending before this entry
+                const T a = val_s[e0 + u - z_a];
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int i = 0; i < V; ++i) acc[t].x[i] = mul_add<true>(a, b[u][t].x[i], acc[t].x[i]);
+                dirty = true;
+            }
+        }
+    }
+    while (row < row_next) close_row();   // rows ending exactly at the chunk end, trailing empty rows
+
+    // whatever is left belongs to row_next, which a later chunk closes
+    if (gl == 0) p.carry_rows[c] = dirty ? row_next : kNoCarry;
+    if (dirty) {
+        T *car = static_cast<T *>(p.carry_vals) + (size_t)c * p.ldcar + gl * V;
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+            if (col_ok[t]) acc[t].store(car + t * G * V, false);
+    }
+}
+
+// One warp per chunk; only the first chunk of each run of carry-outs into the same row works.
+template <typename T>
+__global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeParams p)
+{
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (c >= p.num_chunks) return;
+    const uint32_t row = p.carry_rows[c];
+    if (row == kNoCarry) return;
+    if (c > 0 && p.carry_rows[c - 1] == row) return;
+    // run length: chunks c, c+1, ... carrying into the same row (contiguous by construction)
+    uint32_t len = 1;
+    for (;;) {
+        const uint32_t k = c + len + lane;
+        const bool same = k < p.num_chunks && p.carry_rows[k] == row;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, same);
+        if (m == 0xFFFFFFFFu) {
+            len += 32;
+            continue;
+        }
+        len += __ffs(~m) - 1;
+        break;
+    }
+    const T *car = static_cast<const T *>(p.carry_vals);
+    T *crow = static_cast<T *>(p.C) + (size_t)row * p.ldc;
+    for (uint32_t j = lane; j < p.n; j += 32) {
+        T sum = car[(size_t)c * p.ldcar + j];
+#pragma unroll 8
+        for (uint32_t k = 1; k < len; ++k) sum += car[(size_t)(c + k) * p.ldcar + j];
+        crow[j] = sum + crow[j];   // carries first (they precede the tail in stored order)
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+template <typename T, int V, int G, int NT> static const void *merge_kernel_ptr()
+{
+    return reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT>);
+}
+template <typename T, int V> static const void *merge_kernel_select_gnt(int G, int NT)
+{
+    if (G == 32) {
+        switch (NT) {
+            case 1: return merge_kernel_ptr<T, V, 32, 1>();
+            case 2: return merge_kernel_ptr<T, V, 32, 2>();
+            case 4: return merge_kernel_ptr<T, V, 32, 4>();
+        }
+        return nullptr;
+    }
+    if (NT != 1) return nullptr;
+    switch (G) {
+        case 16: return merge_kernel_ptr<T, V, 16, 1>();
+        case 8: return merge_kernel_ptr<T, V, 8, 1>();
+        case 4: return merge_kernel_ptr<T, V, 4, 1>();
+        case 2: return merge_kernel_ptr<T, V, 2, 1>();
+        case 1: return merge_kernel_ptr<T, V, 1, 1>();
+    }
+    return nullptr;
+}
+static const void *merge_kernel_select(int dtype, Shape sh)
+{
+    if (dtype == BSM_F64) {
+        if (sh.V == 1) return merge_kernel_select_gnt<double, 1>(sh.G, sh.NT);
+        if (sh.V == 2) return merge_kernel_select_gnt<double, 2>(sh.G, sh.NT);
+    } else {
+        if (sh.V == 1) return merge_kernel_select_gnt<float, 1>(sh.G, sh.NT);
+        if (sh.V == 2) return merge_kernel_select_gnt<float, 2>(sh.G, sh.NT);
+        if (sh.V == 4) return merge_kernel_select_gnt<float, 4>(sh.G, sh.NT);
+    }
+    return nullptr;
+}
+
+size_t merge_kernel_smem_bytes(int dtype, Shape sh, int block, uint32_t items)
+{
+    const size_t span = (size_t)(block / 32) * (32 / sh.G) * items;
+    return (span + 4) * dtype_size(dtype) + (span + 4) * 4 + (span + 8) * 4;
+}
+
+int launch_merge_partition(const uint32_t *row_ptr, uint32_t rows, uint32_t nnz, uint32_t items, uint32_t num_chunks,
+                           uint32_t *part_rows, cudaStream_t stream)
+{
+    const uint32_t threads = 256;
+    const uint32_t blocks = (num_chunks + 1 + threads - 1) / threads;
+    merge_partition_kernel<<<blocks, threads, 0, stream>>>(row_ptr, rows, nnz, items, num_chunks, part_rows);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, cudaStream_t stream, int *grid_out)
+{
+    const void *k = merge_kernel_select(dtype, sh);
+    if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_merge: no kernel for this lane shape");
+    const uint32_t groups_per_cta = (uint32_t)(block / 32) * (32 / sh.G);
+    const uint32_t grid = (p.num_chunks + groups_per_cta - 1) / groups_per_cta;
+    if (grid == 0) return BSM_OK;
+    BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MergeParams pc = p;
+    void *args[] = {&pc};
+    BSM_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(block), args, smem, stream));
+    count_launch();
+    if (grid_out) *grid_out = (int)grid;
+    return BSM_OK;
+}
+
+int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream)
+{
+    if (p.num_chunks == 0) return BSM_OK;
+    const uint32_t threads = 256;
+    const uint64_t total_threads = (uint64_t)p.num_chunks * 32;
+    const uint32_t blocks = (uint32_t)((total_threads + threads - 1) / threads);
+    if (dtype == BSM_F64)
+        merge_fixup_kernel<double><<<blocks, threads, 0, stream>>>(p);
+    else
+        merge_fixup_kernel<float><<<blocks, threads, 0, stream>>>(p);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+}  // namespace bsm

@@ -1,0 +1,253 @@
+/*
+ * bsm.h — C ABI of the B200-native Csr x Dense (SpMM / SpMV) path.
+ *
+ * This is the drop-in boundary for ONE reference routine and its operand types:
+ *     Csr<T>::mul_dense(&self, rhs:&Dense<T>) -> Result<Csr<T>,MatErr>
+ *         /root/reference/src/sparse.rs:426-446
+ * plus the sibling front-end Csr<T>::mul_vector (sparse.rs:468-482).
+ * The reference has no FFI of its own (pure Rust, zero dependencies); these entry points are
+ * exactly what a `gpu` module inside the crate binds with `extern "C"`.
+ * Plain pointers and sizes only — no CUDA, torch or C++ types in any signature.
+ *
+ * Conventions
+ *   - every function returns a bsm_status (0 = ok); bsm_last_error_string() describes the
+ *     last failure on the calling thread;
+ *   - `usize` of the reference is uint64_t here (x86-64 / aarch64);
+ *   - handles own device memory (HBM) unless created by a *_borrow function;
+ *   - all work is enqueued on one CUDA stream per process (bsm_set_stream can adopt an
+ *     external one, e.g. a torch stream, passed as an opaque pointer); functions that return
+ *     host data synchronise that stream before returning;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails
+ *     with BSM_ERR_NO_DEVICE / BSM_ERR_CUDA.
+ */
+#ifndef BSM_H
+#define BSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSM_ABI_VERSION 1
+
+typedef struct bsm_csr bsm_csr;     /* device-resident CSR: vals[nnz] T, col_idx[nnz] u32, row_ptr[rows+1] u32 */
+typedef struct bsm_dense bsm_dense; /* device-resident dense, ROW-major, leading dimension ld (elements)       */
+typedef struct bsm_comm bsm_comm;   /* NCCL communicator for the optional all-gather of C row blocks            */
+
+typedef enum bsm_status {
+    BSM_OK = 0,
+    /* maps to MatErr::IncorrectDimensions (src/util.rs:47-55; returned at sparse.rs:427-429, 469-471) */
+    BSM_ERR_INCORRECT_DIMENSIONS = 1,
+    /* operand Csr was not finalised (row_index shorter than rows+1; reference would panic on index) */
+    BSM_ERR_NOT_FINALISED = 2,
+    /* a col_index >= cols (reference: slice-index panic at sparse.rs:437) / MatErr::OutOfBounds */
+    BSM_ERR_OUT_OF_BOUNDS = 3,
+    /* nnz or a dimension does not fit the device's u32 indices */
+    BSM_ERR_INDEX_OVERFLOW = 4,
+    BSM_ERR_INVALID_ARGUMENT = 5,
+    BSM_ERR_DTYPE_MISMATCH = 6,
+    BSM_ERR_CUDA = 7,
+    BSM_ERR_NCCL = 8,
+    BSM_ERR_NO_DEVICE = 9,
+    BSM_ERR_NOT_SUPPORTED = 10
+} bsm_status;
+
+typedef enum bsm_dtype { BSM_F32 = 0, BSM_F64 = 1 } bsm_dtype;
+
+/* kernel family (north_star): warp-per-row vector CSR, or nnz-balanced merge-path */
+typedef enum bsm_algo { BSM_ALGO_AUTO = 0, BSM_ALGO_VECTOR = 1, BSM_ALGO_MERGE = 2 } bsm_algo;
+
+/* bsm_tuning.flags */
+#define BSM_TUNE_A_EVICT_FIRST 0x1u   /* L2 evict-first policy on the TMA bulk copies of col_idx/values */
+#define BSM_TUNE_C_STREAMING   0x2u   /* st.global.cs for C rows                                       */
+#define BSM_TUNE_B_FAR_NOALLOC 0x4u   /* ld.global.nc.L1::no_allocate for |col-row| > far_threshold     */
+#define BSM_TUNE_DEFAULT_FLAGS (BSM_TUNE_A_EVICT_FIRST | BSM_TUNE_C_STREAMING)
+
+/* Launch tuning; all-zero = library heuristics. Used by the bench sweeps and tests. */
+typedef struct bsm_tuning {
+    int32_t algo;            /* bsm_algo                                                            */
+    int32_t col_tile;        /* columns per pass over A (0 = all n in one pass)                     */
+    int32_t rows_per_batch;  /* vector kernel: rows staged per TMA batch (0 = heuristic)            */
+    int32_t stages;          /* vector kernel: TMA pipeline depth (0 = heuristic)                   */
+    int32_t warps_per_cta;   /* compute warps per CTA (0 = heuristic)                               */
+    int32_t ctas_per_sm;     /* persistent grid = SMs x this (0 = heuristic)                        */
+    int32_t merge_items;     /* merge-path: (rows+nnz) items per lane group (0 = heuristic)         */
+    uint32_t flags;          /* BSM_TUNE_* (0 = BSM_TUNE_DEFAULT_FLAGS); bit31 set = take literally */
+    uint32_t far_threshold;  /* for BSM_TUNE_B_FAR_NOALLOC                                          */
+    int32_t prefer_wide_rows;/* 1: full warp per row even when 128-bit loads need fewer lanes       */
+    int32_t reserved[6];
+} bsm_tuning;
+
+/* what the last bsm_spmm* call on this thread actually launched */
+typedef struct bsm_launch_info {
+    int32_t algo;            /* BSM_ALGO_VECTOR or BSM_ALGO_MERGE                                   */
+    int32_t kernels;         /* kernels launched by the call                                        */
+    int32_t vec_elems;       /* elements per lane per load (V)                                      */
+    int32_t lanes_per_row;   /* G                                                                   */
+    int32_t reg_tiles;       /* NT                                                                  */
+    int32_t grid, block;     /* of the main kernel                                                  */
+    int32_t smem_bytes;
+    int32_t rows_per_batch, stages, capacity;
+    int32_t passes;          /* column-tile passes                                                  */
+    int32_t merge_items, merge_chunks;
+    int32_t reserved[4];
+} bsm_launch_info;
+
+/* ------------------------------------------------------------------------------------------
+ * runtime
+ * ---------------------------------------------------------------------------------------- */
+int bsm_abi_version(void);
+/* Select the CUDA device of this process (one process per GPU) and create the stream. */
+int bsm_init(int device);
+int bsm_device_count(int *count);
+/* Adopt an external cudaStream_t (opaque pointer; NULL = back to the library's own stream). */
+int bsm_set_stream(void *cuda_stream);
+int bsm_sync(void);
+const char *bsm_last_error_string(void);
+const char *bsm_status_string(int status);
+int bsm_device_info(int *sm_count, size_t *l2_bytes, size_t *hbm_bytes, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Csr<T> operand  (reference: struct Csr, src/sparse.rs:68-78: v:Vec<T>, col_index:Vec<usize>,
+ * row_index:Vec<usize>; finalised => row_index.len() == rows+1, sparse.rs:206-219)
+ * ---------------------------------------------------------------------------------------- */
+/* Upload a finalised host Csr. Indices are narrowed usize -> u32 ON THE DEVICE; the column
+ * bound is checked there too. Column order inside a row is preserved (may be unsorted / hold
+ * duplicates — the reference never sorts, sparse.rs:237-250). */
+int bsm_csr_upload_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v,
+                       const uint64_t *col_index, const uint64_t *row_index,
+                       uint64_t row_index_len, bsm_csr **out);
+int bsm_csr_upload_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const float *v,
+                       const uint64_t *col_index, const uint64_t *row_index,
+                       uint64_t row_index_len, bsm_csr **out);
+/* Adopt device-resident arrays already in device format (u32 indices). copy=0 borrows the
+ * pointers (caller keeps them alive; each array must be 16-byte aligned and readable up to the
+ * next multiple of 4 entries); copy=1 copies into library-owned HBM. */
+int bsm_csr_from_device(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const void *d_vals,
+                        const uint32_t *d_col_idx, const uint32_t *d_row_ptr, int copy,
+                        bsm_csr **out);
+int bsm_csr_free(bsm_csr *a);
+int bsm_csr_info(const bsm_csr *a, int *dtype, uint64_t *rows, uint64_t *cols, uint64_t *nnz,
+                 uint64_t *max_row_nnz);
+/* device pointers of the three arrays (for zero-copy views, e.g. torch.from_dlpack-free use) */
+int bsm_csr_device_ptrs(const bsm_csr *a, const void **d_vals, const uint32_t **d_col_idx,
+                        const uint32_t **d_row_ptr);
+/* Download to the reference layout (usize indices). Buffers sized nnz / nnz / rows+1. */
+int bsm_csr_download_f64(const bsm_csr *a, double *v, uint64_t *col_index, uint64_t *row_index);
+int bsm_csr_download_f32(const bsm_csr *a, float *v, uint64_t *col_index, uint64_t *row_index);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense<T> operand  (reference: struct Dense, src/dense.rs:4-9: data:Vec<Vec<T>>, COLUMN-major,
+ * data[c][r]; get_dims() = {rows:row_count, cols:col_count}, dense.rs:40-47)
+ * ---------------------------------------------------------------------------------------- */
+/* col_ptrs[c] points at host column c (length rows): the Vec<Vec<T>> as it lies in memory.
+ * The columns are copied to HBM and transposed on the device into the row-major layout the
+ * kernels gather from. */
+int bsm_dense_upload_f64(uint64_t rows, uint64_t cols, const double *const *col_ptrs, bsm_dense **out);
+int bsm_dense_upload_f32(uint64_t rows, uint64_t cols, const float *const *col_ptrs, bsm_dense **out);
+int bsm_dense_alloc(int dtype, uint64_t rows, uint64_t cols, bsm_dense **out);
+/* Borrow an existing row-major device buffer (ld in elements, ld >= cols). */
+int bsm_dense_borrow(int dtype, uint64_t rows, uint64_t cols, void *d_rowmajor, uint64_t ld,
+                     bsm_dense **out);
+int bsm_dense_free(bsm_dense *d);
+int bsm_dense_info(const bsm_dense *d, int *dtype, uint64_t *rows, uint64_t *cols, uint64_t *ld,
+                   void **d_ptr);
+/* Download into host columns (col_ptrs[c] has room for `rows` elements). */
+int bsm_dense_download_f64(const bsm_dense *d, double *const *col_ptrs);
+int bsm_dense_download_f32(const bsm_dense *d, float *const *col_ptrs);
+/* Row-major host copies (tests / C++ callers). dst/src hold rows*cols elements, ld = cols. */
+int bsm_dense_download_rowmajor(const bsm_dense *d, void *dst);
+int bsm_dense_upload_rowmajor(int dtype, uint64_t rows, uint64_t cols, const void *src, bsm_dense **out);
+
+/* ------------------------------------------------------------------------------------------
+ * THE HOT PATH — replaces Csr::mul_dense, src/sparse.rs:426-446
+ * C (rows(A) x cols(B), device-resident, row-major) = A * B.
+ *   A.cols != B.rows                      -> BSM_ERR_INCORRECT_DIMENSIONS (sparse.rs:427-429)
+ *   C dims != (A.rows, B.cols)            -> BSM_ERR_INCORRECT_DIMENSIONS
+ * Summation order: BSM_ALGO_VECTOR walks each row's stored entries in stored order with a
+ * separately rounded multiply and add (sparse.rs:434-439) — bit-identical to the reference.
+ * BSM_ALGO_MERGE uses FMA and splits long rows (deterministic, tolerance-level agreement).
+ * ---------------------------------------------------------------------------------------- */
+int bsm_spmm(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, int algo);
+int bsm_spmm_tuned(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning *tuning);
+int bsm_last_launch_info(bsm_launch_info *info);
+/* cumulative number of this library's kernels launched by this process (bench "gpu_launches") */
+uint64_t bsm_kernel_launch_count(void);
+
+/* Result construction of mul_dense: every output goes through Csr::insert, which drops values
+ * equal to T::default() (sparse.rs:442 -> 222-233; -0.0 dropped, NaN kept), then finalise
+ * (206-219). Device-side count -> scan -> scatter; returns a device Csr (rows x cols of d). */
+int bsm_dense_to_csr(const bsm_dense *d, bsm_csr **out);
+
+/* Host-to-host convenience = the literal reference call: uploads A and B, multiplies, compacts
+ * and returns the zero-dropped result Csr in reference layout. The result arrays are allocated
+ * by the library; release with bsm_host_free. */
+int bsm_mul_dense_host_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v,
+                           const uint64_t *col_index, const uint64_t *row_index,
+                           uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                           const double *const *rhs_col_ptrs, int algo, uint64_t *out_nnz,
+                           double **out_v, uint64_t **out_col_index, uint64_t **out_row_index);
+int bsm_mul_dense_host_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const float *v,
+                           const uint64_t *col_index, const uint64_t *row_index,
+                           uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                           const float *const *rhs_col_ptrs, int algo, uint64_t *out_nnz,
+                           float **out_v, uint64_t **out_col_index, uint64_t **out_row_index);
+void bsm_host_free(void *p);
+
+/* Csr::mul_vector(&self, rhs:&[T], out:&mut [T]) -> Result<(),MatErr>  (sparse.rs:468-482):
+ * host slices in and out, dense result (no zero-drop);
+ * a.cols != rhs_len || a.rows != out_len -> BSM_ERR_INCORRECT_DIMENSIONS (469-471). */
+int bsm_mul_vector_f64(const bsm_csr *a, const double *rhs, uint64_t rhs_len, double *out, uint64_t out_len);
+int bsm_mul_vector_f32(const bsm_csr *a, const float *rhs, uint64_t rhs_len, float *out, uint64_t out_len);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-partitioned multi-GPU (one process per GPU). B is replicated; no data-path collective.
+ * ---------------------------------------------------------------------------------------- */
+/* nnz-balanced contiguous row split: bounds[p] = first row of part p, bounds[parts] = rows.
+ * Pure host function over the reference's row_index (usize). */
+int bsm_partition_rows(const uint64_t *row_index, uint64_t rows, int parts, uint64_t *bounds);
+/* Upload rows [row_begin,row_end) of a host Csr as a device Csr with rebased row_ptr. */
+int bsm_csr_upload_rows_f64(uint64_t rows, uint64_t cols, const double *v, const uint64_t *col_index,
+                            const uint64_t *row_index, uint64_t row_begin, uint64_t row_end,
+                            bsm_csr **out);
+int bsm_csr_upload_rows_f32(uint64_t rows, uint64_t cols, const float *v, const uint64_t *col_index,
+                            const uint64_t *row_index, uint64_t row_begin, uint64_t row_end,
+                            bsm_csr **out);
+/* Optional gathered result: NCCL all-gather(v) of the C row blocks over NVLink.
+ * unique_id is NCCL_UNIQUE_ID_BYTES (128) bytes, created on rank 0 and shipped to the other
+ * ranks by the caller (torch.distributed / any transport). */
+int bsm_comm_unique_id(char id[128]);
+int bsm_comm_init(const char id[128], int nranks, int rank, bsm_comm **out);
+int bsm_comm_free(bsm_comm *c);
+/* full (rows_total x cols, row-major, on every rank) <- concat over ranks of local blocks;
+ * bounds[] as returned by bsm_partition_rows (nranks+1 entries). */
+int bsm_allgather_rows(bsm_comm *c, const bsm_dense *local_block, const uint64_t *bounds, bsm_dense *full);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic workloads generated directly in HBM (bench / test support; counter-based hash so
+ * the CPU oracle regenerates any element independently — see basic_sparse_matrix_b200/gen.py)
+ * ---------------------------------------------------------------------------------------- */
+/* value mode: 0 = "exact" dyadic rationals k/1024 (every product and sum exact in f64),
+ *             1 = "real" uniform [0,1) + offset */
+int bsm_gen_dense(int dtype, uint64_t rows, uint64_t cols, uint64_t seed, int mode, double offset,
+                  bsm_dense **out);
+/* 2-D 5-point / 3-D 7-point Laplacian rows [row_begin,row_end) of the nx*ny(*nz) grid
+ * (nz = 1 for 2-D), diagonal 4 / 6, off-diagonals -1, columns ascending; rebased row_ptr. */
+int bsm_gen_laplacian(int dtype, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t row_begin,
+                      uint64_t row_end, bsm_csr **out);
+/* SPD band, half-bandwidth hb: a_ij = -1/(1+|i-j|), a_ii = 1 + sum_j |a_ij|. */
+int bsm_gen_band(int dtype, uint64_t n, uint64_t hb, uint64_t row_begin, uint64_t row_end, bsm_csr **out);
+/* R-MAT: 2^scale rows/cols, `edges` draws with (a,b,c,d), sorted by (row,col), duplicates
+ * kept; values from the hash in the given mode. */
+int bsm_gen_rmat(int dtype, int scale, uint64_t edges, double a, double b, double c, uint64_t seed,
+                 int mode, bsm_csr **out);
+
+/* raw device memory helpers for callers that keep their own buffers */
+int bsm_l2_flush(void);   /* overwrite a buffer larger than L2 (timing hygiene) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSM_H */

@@ -152,7 +152,10 @@ static size_t FN(get_row_compact)(const OCSR *m, size_t index, int faithful, OEN
     size_t row_start = m->row_index[index];                         /* :255 */
     size_t row_end = (index == m->ri_len - 1) ? m->v_len            /* :256-257 */
                                               : m->row_index[index + 1]; /* :259 */
+    /* Vec::with_capacity(self.dims.cols) (:254); a Vec grows when a row holds more entries than
+     * that (duplicate columns), modelled by sizing the buffer to the larger of the two */
     size_t cap = faithful ? m->cols : (row_end - row_start);
+    if (cap < row_end - row_start) cap = row_end - row_start;
     OENTRY *row = (OENTRY *)malloc((cap ? cap : 1) * sizeof(OENTRY)); /* :254 */
     size_t n = 0;
     for (size_t e = row_start; e < row_end; ++e) {                  /* :261-263 */

@@ -1,0 +1,44 @@
+"""CPU: the C-ABI shared library loads and exports every function include/bsm.h declares."""
+import ctypes
+import os
+import re
+
+from basic_sparse_matrix_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    hdr = open(os.path.join(ROOT, "include", "bsm.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)          # strip comments
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|uint64_t|char)\s*\*?\s*(bsm_[a-z0-9_]+)\s*\(", hdr, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    assert len(names) >= 40
+    for must in ("bsm_spmm", "bsm_csr_upload_f64", "bsm_dense_upload_f64", "bsm_dense_to_csr",
+                 "bsm_mul_dense_host_f64", "bsm_mul_vector_f64", "bsm_partition_rows", "bsm_allgather_rows"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build the native library first (__graft_entry__.build())"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared_functions() if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_abi_version_and_status_strings():
+    L = _lib.lib()
+    assert L.bsm_abi_version() == 1
+    assert L.bsm_status_string(1) == b"IncorrectDimensions"
+    assert L.bsm_status_string(0) == b"ok"
+
+
+def test_python_binding_covers_every_symbol():
+    L = _lib.lib()
+    for n in declared_functions():
+        assert getattr(L, n).argtypes is not None or n in ("bsm_abi_version", "bsm_sync", "bsm_last_error_string",
+                                                           "bsm_kernel_launch_count", "bsm_l2_flush"), n

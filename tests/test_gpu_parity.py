@@ -1,0 +1,290 @@
+"""GPU (-m gpu): parity of the sm_100a kernels against the oracle, through the C ABI.
+
+Bars (north_star / SURVEY §7.3-5):
+  * vector-CSR kernel: BIT-EXACT against the restated sequential sum for ANY f32/f64 input
+    (stored order, separately rounded multiply and add);
+  * merge-path kernel: bit-exact on exactly representable (dyadic) inputs; otherwise
+    |gpu - ref| <= tol * sum_j |a_ij b_jk| with tol = 1e-12 (f64) / 1e-5 (f32);
+  * result Csr (zero-drop + finalise) identical field by field to the oracle's.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_bitwise, assert_tolerance, random_csr, random_dense
+from basic_sparse_matrix_b200 import Csr, Dense, MatErr, MatError, _lib, gen
+from oracle import ref_numpy
+from oracle.ref_cpu import OracleCsr
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+DTYPES = [np.float64, np.float32]
+NS = [1, 2, 3, 10, 31, 32, 33, 64, 128, 130, 256, 300]
+
+
+def host_csr(dims, v, ci, ri):
+    return Csr.from_raw_parts(dims, v, ci, ri)
+
+
+def gpu_product(gpu, dims, v, ci, ri, b, algo, **tune):
+    a = gpu.DeviceCsr.from_host(host_csr(dims, v, ci, ri))
+    bd = gpu.DeviceDense.from_rowmajor(b)
+    t = gpu.make_tuning(algo, **tune) if tune else None
+    c = a.mul_dense(bd, algo=algo, tuning=t)
+    out = c.to_rowmajor()
+    info = gpu.last_launch_info()
+    for h in (a, bd, c):
+        h.close()
+    return out, info
+
+
+# ---- the reference's own tests, through the GPU path --------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_kats(gpu, golden, dtype):
+    """test_dense_mul (sparse.rs:1082-1109) and test_nnz (1153-1178) read as in the reference:
+    build operands with from_data, multiply, assert_eq! against from_data(expected)."""
+    for k in golden["mul_dense"]:
+        d = Dense.from_data(k["dense_columns"], dtype)
+        s = Csr.from_data(k["csr_rows"], dtype)
+        output_ref = Csr.from_data(k["output_rows"], dtype)
+        output = s.mul_dense(d)
+        assert output == output_ref, k["name"]
+        if "nnz" in k:
+            assert output.get_nnz() == k["nnz"]
+        for algo in ("vector", "merge"):
+            assert s.mul_dense(d, algo=algo) == output_ref, (k["name"], algo)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mul_vector_kat(gpu, golden, dtype):
+    k = golden["mul_vector"]                                               # sparse.rs:1501-1529
+    v = np.array(k["v"], dtype)
+    out = np.zeros(5, dtype)
+    with pytest.raises(MatError) as e:
+        Csr.from_data(k["bad_dims_matrix"], dtype).mul_vector(v, out)
+    assert e.value.kind == MatErr.IncorrectDimensions
+    Csr.from_data(k["identity"], dtype).mul_vector(v, out)
+    assert out.tolist() == k["v"]
+    out = np.zeros(2, dtype)
+    Csr.from_data(k["matrix"], dtype).mul_vector(v, out)
+    assert out.tolist() == k["expected"]
+
+
+def test_error_codes(gpu):
+    a = gpu.DeviceCsr.from_host(Csr.from_data([[1.0, 2.0, 3.0]]))
+    b = gpu.DeviceDense.from_rowmajor(np.ones((2, 4)))
+    with pytest.raises(MatError) as e:
+        a.mul_dense(b)
+    assert e.value.kind == MatErr.IncorrectDimensions
+    c = gpu.DeviceDense.alloc(5, 4)
+    b3 = gpu.DeviceDense.from_rowmajor(np.ones((3, 4)))
+    with pytest.raises(MatError):
+        a.mul_dense(b3, out=c)                                             # C has the wrong shape
+    with pytest.raises(_lib.BsmError):
+        a.mul_dense(gpu.DeviceDense.from_rowmajor(np.ones((3, 4), np.float32)))   # dtype mismatch
+    # not finalised -> MatrixNotFinalised; column out of range -> OutOfBounds
+    m = Csr.new((2, 2))
+    m.insert(1.0, 0, 0)
+    with pytest.raises(MatError) as e:
+        gpu.DeviceCsr.from_host(m)
+    assert e.value.kind == MatErr.MatrixNotFinalised
+    bad = Csr.from_raw_parts((2, 2), np.ones(1), np.array([5], np.uint64), np.array([0, 1, 1], np.uint64))
+    with pytest.raises(MatError) as e:
+        gpu.DeviceCsr.from_host(bad)
+    assert e.value.kind == MatErr.OutOfBounds
+
+
+# ---- vector kernel: bit-exact for any input -----------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", NS)
+def test_vector_bitwise_random(gpu, dtype, n):
+    rng = np.random.default_rng(100 + n)
+    m, k = 517, 300
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=7, giant_row=40, giant_len=700)
+    b = random_dense(rng, k, n, dtype)
+    got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "vector")
+    assert info["algo"] == _lib.ALGO_VECTOR
+    assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), f"vector n={n}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vector_tuning_variants_are_bitwise_identical(gpu, dtype):
+    rng = np.random.default_rng(5)
+    m, k, n = 2049, 1000, 64
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=9)
+    b = random_dense(rng, k, n, dtype)
+    want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+    for tune in (dict(rows_per_batch=8), dict(rows_per_batch=64, stages=2), dict(rows_per_batch=1024, stages=1),
+                 dict(col_tile=16), dict(col_tile=32, ctas_per_sm=1), dict(prefer_wide_rows=1),
+                 dict(warps_per_cta=2), dict(flags=_lib.TUNE_LITERAL), dict(flags=7, far_threshold=16)):
+        got, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", **tune)
+        assert_bitwise(got, want, f"tuning {tune}")
+
+
+def test_vector_slow_path_rows_longer_than_a_stage(gpu):
+    rng = np.random.default_rng(9)
+    m, k, n = 64, 5000, 32
+    v, ci, ri = random_csr(rng, m, k, np.float64, mean_len=3, giant_row=17, giant_len=40_000)
+    b = random_dense(rng, k, n, np.float64)
+    got, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "vector")
+    assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), "slow path")
+
+
+# ---- merge-path kernel -------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", NS)
+def test_merge_bitwise_on_exact_inputs(gpu, dtype, n):
+    rng = np.random.default_rng(200 + n)
+    m, k = 700, 256
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=5, empty_frac=0.3, giant_row=333, giant_len=3000, exact=True)
+    b = random_dense(rng, k, n, dtype, exact=True)
+    got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
+    assert info["algo"] == _lib.ALGO_MERGE
+    assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), f"merge exact n={n}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 10, 64, 128])
+def test_merge_within_tolerance_on_real_inputs(gpu, dtype, n):
+    rng = np.random.default_rng(300 + n)
+    m, k = 900, 400
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=6, giant_row=1, giant_len=5000)
+    b = random_dense(rng, k, n, dtype)
+    got, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
+    want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+    scale = ref_numpy.abs_product_sum(v, ci, ri, b)
+    assert_tolerance(got, want, scale, TOL[dtype], f"merge real n={n}")
+
+
+def test_merge_items_variants(gpu):
+    rng = np.random.default_rng(17)
+    m, k, n = 1500, 600, 64
+    v, ci, ri = random_csr(rng, m, k, np.float64, mean_len=4, empty_frac=0.5, giant_row=1499, giant_len=9000, exact=True)
+    b = random_dense(rng, k, n, np.float64, exact=True)
+    want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+    for tune in (dict(merge_items=16), dict(merge_items=64), dict(merge_items=512, warps_per_cta=4),
+                 dict(col_tile=16), dict(prefer_wide_rows=-1)):
+        got, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "merge", **tune)
+        assert_bitwise(got, want, f"merge tuning {tune}")
+
+
+def test_merge_is_deterministic(gpu):
+    rng = np.random.default_rng(23)
+    m, k, n = 800, 500, 64
+    v, ci, ri = random_csr(rng, m, k, np.float64, giant_row=10, giant_len=20_000)
+    b = random_dense(rng, k, n, np.float64)
+    first, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
+    for _ in range(3):
+        again, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
+        assert_bitwise(again, first, "run-to-run")
+
+
+# ---- edge shapes ----------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["vector", "merge", "auto"])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_edge_shapes(gpu, algo, dtype):
+    cases = []
+    cases.append(((1, 1), np.array([2.0]), [0], [0, 1]))                          # 1x1
+    cases.append(((4, 3), np.zeros(0), [], [0, 0, 0, 0, 0]))                      # no entries at all
+    cases.append(((5, 4), np.array([1.0, 2.0, 3.0]), [3, 0, 0], [0, 0, 0, 3, 3, 3]))   # empty rows top and bottom, dup col
+    cases.append(((3, 6), np.arange(1.0, 13.0), [5, 4, 3, 2, 1, 0, 0, 1, 2, 3, 4, 5], [0, 6, 6, 12]))  # unsorted, empty middle
+    cases.append(((2, 2), np.array([1.0, -1.0]), [0, 0], [0, 2, 2]))              # duplicates cancel to exact 0
+    for dims, v, ci, ri in cases:
+        for n in (1, 2, 5, 64):
+            rng = np.random.default_rng(n)
+            b = random_dense(rng, dims[1], n, dtype, exact=True)
+            v_ = v.astype(dtype)
+            got, _ = gpu_product(gpu, dims, v_, np.array(ci, np.uint64), np.array(ri, np.uint64), b, algo)
+            want = ref_numpy.mul_dense_rowmajor(v_, np.array(ci, np.uint64), np.array(ri, np.uint64), b)
+            assert_bitwise(got, want, f"{dims} n={n} {algo}")
+
+
+def test_single_giant_row_auto_uses_merge(gpu):
+    rng = np.random.default_rng(31)
+    a, x = gen.bench_as_written(20_000)          # the reference bench shape: ~99 % of nnz in one row
+    v, ci, ri = a.raw_parts()
+    b = x.to_rowmajor()
+    got, info = gpu_product(gpu, (1000, 1000), v, ci, ri, b, "auto")
+    assert info["algo"] == _lib.ALGO_MERGE
+    assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), "bench as written")   # integers: exact
+
+
+# ---- result Csr: zero-drop + finalise ----------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_result_csr_matches_oracle_field_by_field(gpu, dtype):
+    rng = np.random.default_rng(41)
+    m, k, n = 120, 80, 7
+    v, ci, ri = random_csr(rng, m, k, dtype, exact=True, empty_frac=0.4)
+    b = random_dense(rng, k, n, dtype, exact=True)
+    b[:, 2] = 0                                   # a whole zero output column
+    out = host_csr((m, k), v, ci, ri).mul_dense(Dense.from_data([b[:, c] for c in range(n)], dtype))
+    ref = OracleCsr.from_raw((m, k), v, ci, ri).mul_dense([b[:, c].copy() for c in range(n)])
+    assert out.is_finalised and out.get_dims().rows == m and out.get_dims().cols == n
+    assert_bitwise(out.v, ref.v)
+    assert np.array_equal(out.col_index, ref.col_index) and np.array_equal(out.row_index, ref.row_index)
+    assert out.get_nnz() == ref.get_nnz() < m * n
+
+
+def test_zero_drop_keeps_nan_drops_negative_zero(gpu):
+    d = np.array([[0.0, -0.0, np.nan, 1.0], [-0.0, 0.0, 0.0, 0.0], [2.0, 0.0, np.inf, -3.0]])
+    dd = gpu.DeviceDense.from_rowmajor(d)
+    r = dd.into_csr().to_host()
+    rv, rc, rr = ref_numpy.dense_to_csr(d)
+    assert r.row_index.tolist() == rr.tolist() == [0, 2, 2, 5]
+    assert r.col_index.tolist() == rc.tolist() == [2, 3, 0, 2, 3]
+    assert np.isnan(r.v[0]) and r.v[1:].tolist() == [1.0, 2.0, np.inf, -3.0]
+
+
+def test_compaction_large(gpu):
+    rng = np.random.default_rng(43)
+    d = rng.integers(-1, 2, size=(70_001, 33)).astype(np.float32)    # ~1/3 zeros, crosses scan tiles
+    r = gpu.DeviceDense.from_rowmajor(d).into_csr().to_host()
+    rv, rc, rr = ref_numpy.dense_to_csr(d)
+    assert np.array_equal(r.v, rv) and np.array_equal(r.col_index, rc) and np.array_equal(r.row_index, rr)
+
+
+# ---- host <-> device format conversion -----------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_upload_download_roundtrip(gpu, dtype):
+    rng = np.random.default_rng(47)
+    v, ci, ri = random_csr(rng, 333, 77, dtype)
+    back = gpu.DeviceCsr.from_host(host_csr((333, 77), v, ci, ri)).to_host()
+    assert back == host_csr((333, 77), v, ci, ri)
+    for rows, cols in ((1, 1), (100, 1), (65, 33), (1000, 10), (31, 130)):
+        d = Dense.from_data([rng.standard_normal(rows).astype(dtype) for _ in range(cols)], dtype)
+        dev = gpu.DeviceDense.from_host(d)
+        assert dev.to_host() == d                                       # column-major round trip
+        assert np.array_equal(dev.to_rowmajor(), d.to_rowmajor())       # device layout is row-major
+
+
+def test_row_slice_upload(gpu):
+    rng = np.random.default_rng(53)
+    m, k, n = 400, 120, 16
+    v, ci, ri = random_csr(rng, m, k, np.float64)
+    b = random_dense(rng, k, n, np.float64)
+    want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+    bounds = gpu.partition_rows(ri, 3).astype(int)
+    bd = gpu.DeviceDense.from_rowmajor(b)
+    parts = []
+    for p in range(3):
+        a = gpu.DeviceCsr.from_host(host_csr((m, k), v, ci, ri), int(bounds[p]), int(bounds[p + 1]))
+        parts.append(a.mul_dense(bd, algo="vector").to_rowmajor())
+    assert_bitwise(np.concatenate(parts, axis=0), want, "row-partitioned product")
+
+
+# ---- device generators == numpy generators --------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_device_generators_match_numpy(gpu, dtype):
+    for (nx, ny, nz, r0, r1) in ((9, 7, 1, 0, None), (6, 5, 4, 17, 101)):
+        a = gpu.DeviceCsr.laplacian(nx, ny, nz, r0, r1, dtype).to_host()
+        v, ci, ri, dims = gen.laplacian(nx, ny, nz, r0, r1, dtype)
+        assert a == host_csr(dims, v, ci, ri)
+    a = gpu.DeviceCsr.band(300, 32, 10, 290, dtype).to_host()
+    v, ci, ri, dims = gen.band(300, 32, 10, 290, dtype)
+    assert a == host_csr(dims, v, ci, ri)
+    for mode in (gen.MODE_EXACT, gen.MODE_REAL, gen.MODE_EXACT_SMALL):
+        a = gpu.DeviceCsr.rmat(10, 30_000, seed=3, mode=mode, dtype=dtype).to_host()
+        v, ci, ri, dims = gen.rmat(10, 30_000, seed=3, mode=mode, dtype=dtype)
+        assert a == host_csr(dims, v, ci, ri)
+        d = gpu.DeviceDense.generate(123, 17, seed=4, mode=mode, offset=0.5, dtype=dtype).to_rowmajor()
+        assert np.array_equal(d, gen.dense_rows(123, 17, 4, mode, 0.5, dtype))

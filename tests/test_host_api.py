@@ -1,0 +1,111 @@
+"""CPU: the host-side mirror of the reference interface (Csr / Dense / MatDim / MatErr) and the
+loud failure of the product path when no CUDA device is usable (no CPU fallback)."""
+import numpy as np
+import pytest
+
+from basic_sparse_matrix_b200 import Csr, Dense, MatDim, MatErr, MatError
+from basic_sparse_matrix_b200 import _lib
+
+
+def test_structure_kats(golden):
+    for k in golden["structure"]:
+        if "data" not in k:
+            continue
+        m = Csr.from_data(k["data"])
+        assert m.v.tolist() == k["v"] and m.col_index.tolist() == k["col_index"]
+        assert m.row_index.tolist() == k["row_index"] and m.is_finalised
+
+
+def test_create_mat_by_insert(golden):
+    k = [s for s in golden["structure"] if s["name"] == "create_mat_by_insert"][0]
+    b = Csr.new(tuple(k["dims"]))
+    for v, r, c in k["inserts"]:
+        b.insert(v, r, c)
+    assert b.finalise() == Csr.from_data(k["equals_from_data"])
+
+
+def test_dense_kats(golden):
+    init, get_col = golden["dense"]
+    a = Dense.new_default_with_dims(*init["new_default_with_dims"])       # (cols, rows)  dense.rs:13
+    assert a == Dense.from_data(init["equals_from_data_columns"])
+    assert a.get_dims() == MatDim(rows=7, cols=5)
+    d = Dense.from_data(get_col["columns"])
+    assert d.get_col(2).tolist() == get_col["get_col_2"]                   # dense.rs:82-90
+
+
+def test_insert_rules():
+    m = Csr.new((2, 2))
+    m.insert(0.0, 0, 0)
+    m.insert(-0.0, 0, 1)
+    m.insert(float("nan"), 1, 0)
+    m = m.finalise()
+    assert m.get_nnz() == 1 and m.row_index.tolist() == [0, 0, 1]
+    with pytest.raises(MatError) as e:
+        m.insert(1.0, 1, 1)
+    assert e.value.kind == MatErr.MatrixFinalised
+    # out-of-order rows are appended to the current last row
+    m = Csr.new((4, 4))
+    for v, r, c in [(1, 2, 1), (2, 0, 3), (3, 3, 0), (4, 1, 1)]:
+        m.insert(v, r, c)
+    m = m.finalise()
+    assert m.col_index.tolist() == [1, 3, 0, 1] and m.row_index.tolist() == [0, 0, 0, 2, 4]
+
+
+def test_host_csr_matches_oracle_construction():
+    from oracle.ref_cpu import OracleCsr
+    rng = np.random.default_rng(0)
+    data = rng.integers(-2, 3, size=(9, 7)).astype(np.float64)
+    h, o = Csr.from_data(data.tolist()), OracleCsr.from_data(data, np.float64)
+    assert np.array_equal(h.v, o.v) and np.array_equal(h.col_index, o.col_index)
+    assert np.array_equal(h.row_index, o.row_index)
+    # random (possibly out-of-order) inserts
+    h, o = Csr.new((6, 6)), OracleCsr.new((6, 6), np.float64)
+    for _ in range(40):
+        v, r, c = float(rng.integers(0, 3)), int(rng.integers(0, 6)), int(rng.integers(0, 6))
+        h.insert(v, r, c)
+        o.insert(v, r, c)
+    h.finalise()
+    o.finalise()
+    assert np.array_equal(h.v, o.v) and np.array_equal(h.col_index, o.col_index)
+    assert np.array_equal(h.row_index, o.row_index)
+
+
+def test_get_row_compact():
+    m = Csr.from_data([[8, 0, 2, 0, 0], [0, 0, 5, 0, 0], [0, 0, 0, 0, 0]])
+    row = m.get_row_compact(0)
+    assert [(e.v, e.col_index, e.row_index) for e in row] == [(8.0, 0, 0), (2.0, 2, 0)]
+    assert m.get_row_compact(2) == []
+
+
+def test_matdim():
+    d = MatDim.of((3, 4))
+    assert d.rows == 3 and d.cols == 4 and d.transpose() == MatDim(4, 3) and tuple(d) == (3, 4)
+    assert str(d) == "(rows: 3, cols: 4)"
+
+
+def test_dimension_error_is_raised_before_any_device_work():
+    m = Csr.from_data([[1, 2, 3]])
+    with pytest.raises(MatError) as e:
+        m.mul_dense(Dense.from_data([[1, 2]]))                              # sparse.rs:427-429
+    assert e.value.kind == MatErr.IncorrectDimensions
+    out = np.zeros(5)
+    with pytest.raises(MatError) as e:
+        Csr.from_data([[0, 0, 0, 0]] * 3).mul_vector(np.arange(5.0), out)   # sparse.rs:469-471
+    assert e.value.kind == MatErr.IncorrectDimensions
+
+
+def test_integer_dtype_is_rejected_not_emulated():
+    m = Csr.from_data([[1, 2]], dtype=np.int32)
+    with pytest.raises(TypeError):
+        m.mul_dense(Dense.from_data([[1, 2]], dtype=np.int32))
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a usable GPU the product path must fail loudly."""
+    from basic_sparse_matrix_b200 import gpu
+    if gpu.device_count() > 0:
+        pytest.skip("a CUDA device is present; the fallback check only applies to CPU-only hosts")
+    m = Csr.from_data([[1.0, 2.0]])
+    with pytest.raises(_lib.BsmError) as e:
+        m.mul_dense(Dense.from_data([[1.0, 2.0]]))
+    assert e.value.status == _lib.BSM_ERR_NO_DEVICE
