@@ -1,0 +1,515 @@
+#!/usr/bin/env python3
+"""bench.py — the reference's headline metric on B200: SpMM GFLOP/s + effective HBM GB/s
+(% of the measured roofline) for Csr x Dense, next to the reference's CPU path on the host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3]): 3-D 7-point Laplacian on a 256^3 grid (16 777 216 rows,
+117 047 296 nnz) x dense 16 777 216 x 128, f64, row-partitioned over the N GPUs with nnz-balanced
+splits and B replicated (strong scaling: the problem is fixed, each rank owns a row block, no
+data-path collective).  A "step" is one pass of the hot path (one `Csr::mul_dense`) over the
+matrix.  `value` times the device-resident path with CUDA events; `e2e` times the same product
+through the reference-facing C-ABI calls from HOST buffers (upload A rows, upload B columns with
+the column-major -> row-major transpose, multiply, download C columns).  Operands are far larger
+than L2 (126 MB), so consecutive steps cannot hit in cache (no explicit flush needed).
+
+One JSON line is printed by rank 0.  `--impl reference` times the reference's own CPU
+implementation (the C restatement in oracle/, single-threaded like the Rust original) on the
+host cores for the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SpMM GFLOP/s (2*nnz*ncols; with effective HBM GB/s and fraction of the measured HBM roofline)"
+
+WORKLOADS = {
+    # name: (kind, params, n, dtype)
+    "laplace3d_256_n128_f64": ("laplace3d", dict(g=256), 128, "f64"),     # BASELINE configs[3] — the headline
+    "laplace3d_256_n64_f64": ("laplace3d", dict(g=256), 64, "f64"),       # north_star target case (>=100M nnz x 64)
+    "laplace2d_2048_n1_f64": ("laplace2d", dict(g=2048), 1, "f64"),       # configs[1] SpMV
+    "rmat20_n64_f64": ("rmat", dict(scale=20, edges=100 << 20), 64, "f64"),   # configs[2]
+    "rmat20_n64_f32": ("rmat", dict(scale=20, edges=100 << 20), 64, "f32"),
+    "band_1m_hb32_n32_f32": ("band", dict(n=1 << 20, hb=32), 32, "f32"),  # configs[4] GPU side
+    "band_1m_hb32_n1_f32": ("band", dict(n=1 << 20, hb=32), 1, "f32"),
+}
+DEFAULT_WORKLOAD = "laplace3d_256_n128_f64"
+NP_DTYPE = {"f64": np.float64, "f32": np.float32}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def bytes_min(rows, nnz, k_ref, n, s):
+    """Algorithmic bytes per launch: values + u32 col_idx, u32 row_ptr, the B rows
+    actually referenced, C written once."""
+    return nnz * (s + 4) + (rows + 1) * 4 + k_ref * n * s + rows * n * s
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {}
+        for nm in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap", "HwPowerBrakeSlowdown"):
+            v = getattr(nv, "nvmlClocksEventReason" + nm, None) or getattr(nv, "nvmlClocksThrottleReason" + nm, None)
+            if v is not None:
+                names[v] = nm
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(1.0)
+        snake = {"HwSlowdown": "hw_slowdown", "HwThermalSlowdown": "hw_thermal_slowdown",
+                 "SwThermalSlowdown": "sw_thermal_slowdown", "SwPowerCap": "sw_power_cap",
+                 "HwPowerBrakeSlowdown": "hw_power_brake_slowdown"}
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(snake[r] for r in self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# workload construction (device-side generators; host side regenerates from the same hash)
+# ---------------------------------------------------------------------------------------------
+def host_row_index(kind, prm):
+    """Row pointer of the FULL matrix in the reference layout (usize), for the nnz-balanced split."""
+    from basic_sparse_matrix_b200 import gen
+    if kind == "laplace3d":
+        counts = gen.laplacian_row_counts(prm["g"], prm["g"], prm["g"])
+    elif kind == "laplace2d":
+        counts = gen.laplacian_row_counts(prm["g"], prm["g"], 1)
+    elif kind == "band":
+        i = np.arange(prm["n"], dtype=np.int64)
+        counts = np.minimum(i, prm["hb"]) + 1 + np.minimum(prm["n"] - 1 - i, prm["hb"])
+    else:
+        return None
+    ri = np.zeros(len(counts) + 1, dtype=np.uint64)
+    np.cumsum(counts, out=ri[1:])
+    return ri
+
+
+def make_device_csr(gpu, kind, prm, dtype, r0=0, r1=None):
+    if kind == "laplace3d":
+        return gpu.DeviceCsr.laplacian(prm["g"], prm["g"], prm["g"], r0, r1, dtype)
+    if kind == "laplace2d":
+        return gpu.DeviceCsr.laplacian(prm["g"], prm["g"], 1, r0, r1, dtype)
+    if kind == "band":
+        return gpu.DeviceCsr.band(prm["n"], prm["hb"], r0, r1, dtype)
+    if kind == "rmat":
+        from basic_sparse_matrix_b200 import gen
+        return gpu.DeviceCsr.rmat(prm["scale"], prm["edges"], seed=3, mode=gen.MODE_EXACT, dtype=dtype)
+    raise ValueError(kind)
+
+
+def k_ref_of(kind, prm, rows_total, r0, r1):
+    """Distinct B rows referenced by rows [r0,r1)."""
+    if kind == "laplace3d":
+        reach = prm["g"] * prm["g"]
+    elif kind == "laplace2d":
+        reach = prm["g"]
+    elif kind == "band":
+        reach = prm["hb"]
+    else:
+        return rows_total
+    return min(rows_total, r1 + reach) - max(0, r0 - reach)
+
+
+def time_device_steps(torch, A, B, C, steps, warmup, tuning=None, barrier=None):
+    """W untimed + K timed launches on torch's current stream; per-launch CUDA events."""
+    for _ in range(warmup):
+        A.mul_dense(B, out=C, tuning=tuning)
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
+        A.mul_dense(B, out=C, tuning=tuning)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return total_ms, per
+
+
+def run_extra(torch, gpu, name, steps, warmup, peak):
+    """Secondary single-GPU workloads (kernel-only numbers, reported under other_workloads)."""
+    from basic_sparse_matrix_b200 import gen
+    kind, prm, n, dt = WORKLOADS[name]
+    dtype = NP_DTYPE[dt]
+    s = np.dtype(dtype).itemsize
+    A = make_device_csr(gpu, kind, prm, dtype)
+    ai = A.info()
+    B = gpu.DeviceDense.generate(ai["cols"], n, seed=4, mode=gen.MODE_EXACT, dtype=dtype)
+    C = gpu.DeviceDense.alloc(ai["rows"], n, dtype)
+    total_ms, per = time_device_steps(torch, A, B, C, steps, warmup)
+    info = gpu.last_launch_info()
+    t = total_ms / steps * 1e-3
+    bm = bytes_min(ai["rows"], ai["nnz"], ai["cols"], n, s)
+    out = {"workload": name, "rows": ai["rows"], "nnz": ai["nnz"], "n": n, "dtype": dt,
+           "algo": "merge" if info["algo"] == 2 else "vector", "ms_per_step": round(total_ms / steps, 4),
+           "ms_best": round(min(per), 4), "gflops": round(2.0 * ai["nnz"] * n / t / 1e9, 1),
+           "eff_gbs": round(bm / t / 1e9, 1), "roofline_frac": round(bm / t / 1e9 / peak, 4),
+           "kernels_per_step": info["kernels"]}
+    for h in (A, B, C):
+        h.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline = the reference's CPU path (C restatement, 1 thread) on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(kind, prm, n, dtype, budget_s, b_host_cols=None, fixed_rows=None):
+    """Time the faithful restatement of Csr::mul_dense on a contiguous row sample of the workload.
+    Returns (gflops, seconds, sample_rows, sample_nnz, description)."""
+    from basic_sparse_matrix_b200 import gen
+    from oracle.ref_cpu import OracleCsr
+    if kind not in ("laplace3d", "laplace2d"):
+        raise ValueError("cpu sample implemented for the Laplacian workloads")
+    g = prm["g"]
+    gz = g if kind == "laplace3d" else 1
+    rows_total = g * g * gz
+    reach = g * g if kind == "laplace3d" else g
+    start = (rows_total // 2) // reach * reach          # interior block, aligned to a plane / grid line
+
+    def run(nrows):
+        r0, r1 = start, min(rows_total, start + nrows)
+        v, ci, ri, _ = gen.laplacian(g, g, gz, r0, r1, dtype)
+        cmin, cmax = int(ci.min()), int(ci.max()) + 1
+        if b_host_cols is not None:
+            cols = [c[cmin:cmax] for c in b_host_cols]
+        else:
+            blk = gen.dense_rows(rows_total, n, 5, gen.MODE_EXACT, 0.0, dtype, row_ids=np.arange(cmin, cmax))
+            cols = [np.ascontiguousarray(blk[:, c]) for c in range(n)]
+        # same arithmetic with rebased column indices; dims.cols stays the FULL k so the per-row
+        # Vec::with_capacity(dims.cols) of get_row_compact (sparse.rs:254) costs what it costs
+        a = OracleCsr.from_raw((r1 - r0, rows_total), v, ci - np.uint64(cmin), ri)
+        t, _ = a.time_mul_dense_rows(cols, 0, r1 - r0, faithful=True, rhs_row_count=rows_total)
+        return t, r1 - r0, int(ri[-1])
+
+    if fixed_rows is not None:
+        t, nr, nnz = run(fixed_rows)
+    else:
+        t, nr, nnz = run(4096)                           # calibrate
+        want = int(min(rows_total - start, max(4096, 4096 * budget_s / max(t, 1e-6))))
+        want = min(want, 1 << 21)
+        if want > 8192:
+            t, nr, nnz = run(want)
+    gf = 2.0 * nnz * n / t / 1e9
+    desc = (f"rows [{start},{start + nr}) of the workload ({nr} rows, {nnz} nnz) x {n} cols, faithful C restatement of "
+            f"src/sparse.rs:426-446 incl. per-row Vec::with_capacity(cols) and the zero-dropping result Csr, 1 thread")
+    return gf, t, nr, nnz, desc
+
+
+def main_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/ C port; the
+    Rust original cannot be built here), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind, prm, n, dt = WORKLOADS[args.workload]
+    dtype = NP_DTYPE[dt]
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    # size one step's sample from a calibration run, then time W + K steps of that sample
+    _, t_cal, _, _, _ = cpu_reference_sample(kind, prm, n, dtype, 0.0, fixed_rows=2048)
+    rows_per_step = int(max(1024, min(1 << 20, 2048 * budget / max(t_cal, 1e-6))))
+    times, nnz_s, desc = [], 0, ""
+    for i in range(args.warmup + args.steps):
+        gf, t, nr, nnz_s, desc = cpu_reference_sample(kind, prm, n, dtype, 0.0, fixed_rows=rows_per_step)
+        if i >= args.warmup:
+            times.append(t)
+    t = sum(times) / len(times)
+    value = 2.0 * nnz_s * n / t / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": "GFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": dt, "data": "synthetic",
+            "config": {"workload": args.workload, "note": "each step = one bounded row sample of the workload"},
+            "cpu_baseline": {"value": round(value, 5), "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": desc},
+            "e2e": {"value": round(value, 5), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="also time the optional NCCL all-gather of C row blocks")
+    ap.add_argument("--algo", default="auto")
+    ap.add_argument("--tune", default="", help="k=v,k=v overrides of bsm_tuning (sweeps)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from basic_sparse_matrix_b200 import Dense, gen, gpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    barrier = (lambda: dist.barrier()) if world > 1 else None
+    gpu.init(local)
+    gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+    peak, peak_src = load_peaks()
+
+    kind, prm, n, dt = WORKLOADS[args.workload]
+    dtype = NP_DTYPE[dt]
+    s = np.dtype(dtype).itemsize
+    tuning = None
+    if args.tune or args.algo != "auto":
+        kw = {k: int(v, 0) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}
+        tuning = gpu.make_tuning(args.algo, **kw)
+
+    # ---- operands: nnz-balanced row block of A on this rank, B replicated ---------------------
+    ri_full = host_row_index(kind, prm)
+    if ri_full is not None:
+        rows_total, nnz_total = len(ri_full) - 1, int(ri_full[-1])
+        bounds = gpu.partition_rows(ri_full, world).astype(np.int64)
+        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+        A = make_device_csr(gpu, kind, prm, dtype, r0, r1)
+    else:   # R-MAT: generated whole on the device; single-GPU only
+        if world > 1:
+            raise SystemExit("the R-MAT workload is generated on one device; run it with --gpus 1")
+        A = make_device_csr(gpu, kind, prm, dtype)
+        rows_total, nnz_total = A.info()["rows"], A.info()["nnz"]
+        bounds = np.array([0, rows_total], np.int64)
+        r0, r1 = 0, rows_total
+    ai = A.info()
+    B = gpu.DeviceDense.generate(ai["cols"], n, seed=5, mode=gen.MODE_EXACT, dtype=dtype)
+    C = gpu.DeviceDense.alloc(ai["rows"], n, dtype)
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    launches0 = gpu.kernel_launch_count()
+    for _ in range(args.warmup):
+        A.mul_dense(B, out=C, tuning=tuning)
+    torch.cuda.synchronize()
+    launches_w = gpu.kernel_launch_count()
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
+    for i in range(args.steps):
+        A.mul_dense(B, out=C, tuning=tuning)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    clocks = sampler.stop()
+    launches = gpu.kernel_launch_count() - launches_w
+    info = gpu.last_launch_info()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    t_step = total_ms_max / args.steps * 1e-3
+    value = 2.0 * nnz_total * n / t_step / 1e9
+
+    # roofline of the dominant kernel on this rank (per launch)
+    kref = k_ref_of(kind, prm, rows_total, r0, r1)
+    bm_rank = bytes_min(ai["rows"], ai["nnz"], kref, n, s)
+    t_launch = total_ms / args.steps * 1e-3 / max(1, info["passes"])
+    achieved = bm_rank / max(1, info["passes"]) / t_launch / 1e9 if info["passes"] else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload if world == 1 else "", None)
+        except Exception:
+            traffic = None
+    bm_total = bytes_min(rows_total, nnz_total, rows_total, n, s)
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic,
+                "kernel": ("spmm_rows_kernel" if info["algo"] == 1 else "spmm_merge_kernel"),
+                "algorithmic_bytes_per_launch": int(bm_rank / max(1, info["passes"])),
+                "launch_ms_avg": round(t_launch * 1e3, 4), "launch_ms_best": round(min(per) / max(1, info["passes"]), 4),
+                "peak_source": peak_src}
+
+    # ---- optional gathered result (the only collective of the path) ---------------------------------
+    gather = None
+    if args.gather and world > 1:
+        uid = [gpu.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = gpu.Comm.init(uid[0], world, rank)
+        full = gpu.DeviceDense.alloc(rows_total, n, dtype)
+        comm.allgather_rows(C, bounds.astype(np.uint64), full)       # warm-up (NCCL channel setup)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        comm.allgather_rows(C, bounds.astype(np.uint64), full)
+        e1.record()
+        torch.cuda.synchronize()
+        g_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
+        gather = {"allgather_ms": round(float(g_ms.item()), 3), "bytes_received_per_gpu": int((rows_total - ai["rows"]) * n * s)}
+        full.close()
+        comm.close()
+
+    # ---- end to end through the reference-facing C-ABI calls, from pinned HOST buffers --------------------
+    e2e = None
+    host_cols = None
+    if not args.no_e2e:
+        from basic_sparse_matrix_b200 import Csr
+        # host operands in the REFERENCE layout: Csr fields (usize indices) and Dense columns
+        hA = A.to_host()                                    # rows [r0,r1) as a finalised Csr
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        hv, hci, hri = (pin(x) for x in hA.raw_parts())
+        hA = Csr.from_raw_parts((ai["rows"], ai["cols"]), hv, hci, hri)
+        host_cols = [torch.empty(ai["cols"], dtype=torch.float64 if dt == "f64" else torch.float32).pin_memory().numpy()
+                     for _ in range(n)]
+        B.to_host(Dense.from_columns_nocopy(host_cols))     # the host copy of B (outside the timed region)
+        out_cols = [torch.empty(ai["rows"], dtype=torch.float64 if dt == "f64" else torch.float32).pin_memory().numpy()
+                    for _ in range(n)]
+        hB, hC = Dense.from_columns_nocopy(host_cols), Dense.from_columns_nocopy(out_cols)
+        h2d = hv.nbytes + hci.nbytes + hri.nbytes + sum(c.nbytes for c in host_cols)
+        d2h = sum(c.nbytes for c in out_cols)
+
+        def e2e_step():
+            a_d = gpu.DeviceCsr.from_host(hA)               # H2D values + usize indices, narrowed on device
+            b_d = gpu.DeviceDense.from_host(hB)             # H2D columns + transpose to row-major
+            c_d = a_d.mul_dense(b_d, tuning=tuning)
+            c_d.to_host(hC)                                 # transpose back + D2H columns (synchronises)
+            for h in (a_d, b_d, c_d):
+                h.close()
+
+        e2e_step()                                          # warm-up
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.e2e_steps)):
+            e2e_step()
+        torch.cuda.synchronize()
+        te = (time.perf_counter() - t0) / max(1, args.e2e_steps)
+        te_t = torch.tensor([te], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+        te = float(te_t.item())
+        # result check of the e2e path against the device-resident product
+        chk = np.array_equal(out_cols[0][:1000], C.to_rowmajor()[:1000, 0]) if ai["rows"] >= 1000 else True
+        e2e = {"value": round(2.0 * nnz_total * n / te / 1e9, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": round(te * 1e3, 2), "steps": max(1, args.e2e_steps),
+               "matches_device_path": bool(chk),
+               "path": "bsm_csr_upload + bsm_dense_upload (col-major -> row-major) + bsm_spmm + bsm_dense_download, pinned host buffers"}
+        del out_cols
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's CPU path on a bounded sample ------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and kind in ("laplace3d", "laplace2d"):
+        gf, t, nr, nnz_s, desc = cpu_reference_sample(kind, prm, n, dtype, 12.0, b_host_cols=host_cols)
+        cpu = {"value": round(gf, 5), "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": desc,
+               "seconds": round(t, 2), "host_cores_available": os.cpu_count()}
+
+    # ---- free the headline operands, then the secondary workloads (N=1 only) ----------------------------
+    for h in (A, B, C):
+        h.close()
+    host_cols = None
+    extras = []
+    if rank == 0 and world == 1 and not args.no_extras:
+        for name in WORKLOADS:
+            if name == args.workload:
+                continue
+            try:
+                extras.append(run_extra(torch, gpu, name, 10, 3, peak))
+            except Exception as ex:   # keep the headline line even if a side workload fails
+                extras.append({"workload": name, "error": str(ex)[:200]})
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(total_ms_max / args.steps, 4), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": dt, "data": "synthetic",
+                "config": {"workload": args.workload, "rows": rows_total, "nnz": nnz_total, "ncols": n,
+                           "partition": f"nnz-balanced row blocks x{world}, B replicated, no data-path collective",
+                           "l2": "operands >> L2 (126 MB), no flush needed", "values": "exact dyadic (k/1024), hash-generated on device",
+                           "algo": "vector" if info["algo"] == 1 else "merge", "launch": info},
+                "effective_gbs": round(bm_total / t_step / 1e9, 1),
+                "roofline_frac_job": round(bm_total / t_step / 1e9 / (peak * world), 4),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "ms_per_step_best": round(min(per), 4), "gather": gather, "other_workloads": extras}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
