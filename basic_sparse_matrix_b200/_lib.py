@@ -34,7 +34,6 @@ ALGO_NAMES = {"auto": ALGO_AUTO, "vector": ALGO_VECTOR, "merge": ALGO_MERGE}
 
 TUNE_A_EVICT_FIRST = 0x1
 TUNE_C_STREAMING = 0x2
-TUNE_B_FAR_NOALLOC = 0x4
 TUNE_LITERAL = 0x80000000
 
 
@@ -48,10 +47,10 @@ class BsmError(RuntimeError):
 
 class Tuning(C.Structure):
     _fields_ = [
-        ("algo", C.c_int32), ("col_tile", C.c_int32), ("rows_per_batch", C.c_int32),
+        ("algo", C.c_int32), ("col_tile", C.c_int32), ("rows_per_slice", C.c_int32),
         ("stages", C.c_int32), ("warps_per_cta", C.c_int32), ("ctas_per_sm", C.c_int32),
-        ("merge_items", C.c_int32), ("flags", C.c_uint32), ("far_threshold", C.c_uint32),
-        ("prefer_wide_rows", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("merge_items", C.c_int32), ("flags", C.c_uint32), ("rows_per_warp", C.c_int32),
+        ("prefer_wide_rows", C.c_int32), ("sync_rows", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -59,9 +58,10 @@ class LaunchInfo(C.Structure):
     _fields_ = [
         ("algo", C.c_int32), ("kernels", C.c_int32), ("vec_elems", C.c_int32),
         ("lanes_per_row", C.c_int32), ("reg_tiles", C.c_int32), ("grid", C.c_int32),
-        ("block", C.c_int32), ("smem_bytes", C.c_int32), ("rows_per_batch", C.c_int32),
+        ("block", C.c_int32), ("smem_bytes", C.c_int32), ("rows_per_slice", C.c_int32),
         ("stages", C.c_int32), ("capacity", C.c_int32), ("passes", C.c_int32),
-        ("merge_items", C.c_int32), ("merge_chunks", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("merge_items", C.c_int32), ("merge_chunks", C.c_int32), ("rows_per_warp", C.c_int32),
+        ("sync_rows", C.c_int32), ("col_tile", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
     def as_dict(self):

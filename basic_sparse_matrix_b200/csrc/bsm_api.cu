@@ -75,6 +75,40 @@ static int alloc_csr(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, bsm_
     return BSM_OK;
 }
 
+// Stencil-like matrices (Laplacians on a grid) touch B at fixed column offsets from the diagonal:
+// +-1, +-nx, +-nx*ny. The smallest offset above 1 ("row stride") tells the vector kernel how many
+// consecutive rows one warp should own so that the warps of a CTA sweep adjacent grid lines and
+// share those B rows through L1. Sampled from three interior rows; 0 when the matrix is not of that
+// shape. A performance hint only: any value is correct.
+static int detect_row_stride(bsm_csr *a)
+{
+    a->row_stride = 0;
+    if (a->rows < 4096 || a->max_row_nnz < 3 || a->max_row_nnz > 64) return BSM_OK;
+    uint32_t found = 0;
+    for (int q = 1; q <= 3; ++q) {
+        const uint64_t r = a->rows / 4 * q;
+        uint32_t rp[2];
+        BSM_CUDA(cudaMemcpyAsync(rp, a->row_ptr + r, 8, cudaMemcpyDeviceToHost, g_rt.stream));
+        BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
+        const uint32_t len = rp[1] - rp[0];
+        if (len < 3 || len > 64) return BSM_OK;
+        uint32_t cols[64];
+        BSM_CUDA(cudaMemcpyAsync(cols, a->col_idx + rp[0], len * 4, cudaMemcpyDeviceToHost, g_rt.stream));
+        BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
+        std::sort(cols, cols + len);
+        const uint32_t med = cols[len / 2];
+        uint32_t stride = 0;
+        for (uint32_t i = 0; i < len; ++i) {
+            const uint32_t d = cols[i] > med ? cols[i] - med : med - cols[i];
+            if (d > 1 && (stride == 0 || d < stride)) stride = d;
+        }
+        if (stride < 16 || stride > 16384 || (found && stride != found)) return BSM_OK;
+        found = stride;
+    }
+    a->row_stride = found;
+    return BSM_OK;
+}
+
 static int compute_stats(bsm_csr *a)
 {
     uint32_t *d = nullptr;
@@ -87,7 +121,7 @@ static int compute_stats(bsm_csr *a)
     BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
     if (h[1]) return fail(BSM_ERR_INVALID_ARGUMENT, "row_index is not non-decreasing");
     a->max_row_nnz = h[0];
-    return BSM_OK;
+    return detect_row_stride(a);
 }
 
 template <typename T>
@@ -298,6 +332,7 @@ static Shape pick_shape(uint32_t n, uint64_t ldb, uint64_t ldc, uint64_t col0, c
     return sh;
 }
 
+// Geometry of the vector kernel for one column pass (see spmm_rows.cu).
 static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags)
 {
     const size_t s = dtype_size(a->dtype);
@@ -307,16 +342,20 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
     tile = std::min<uint32_t>(tile, 32u * vmax * 4u);   // widest shape one pass can hold in registers
     if (tile < n_total && tile % vmax) tile = std::max<uint32_t>(vmax, tile / vmax * vmax);
     const double mean = a->rows ? (double)a->nnz / (double)a->rows : 0.0;
-    const int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 8) : 8;
     int passes = 0;
     g_info = bsm_launch_info();
     g_info.algo = BSM_ALGO_VECTOR;
+    g_info.col_tile = (int)tile;
     for (uint32_t col0 = 0; col0 < n_total; col0 += tile, ++passes) {
         const uint32_t n = std::min(tile, n_total - col0);
         const char *bp = (const char *)b->data + (size_t)col0 * s;
         char *cp = (char *)c->data + (size_t)col0 * s;
         Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows != 0);
-        const uint32_t rows_per_pass = (uint32_t)nw * (32u / sh.G);
+        const uint32_t rpp = 32u / (uint32_t)sh.G;                 // rows side by side in one warp
+        const uint32_t rq = std::max(4u, rpp);                     // slice granularity (rpp is a power of two)
+        int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 16) : 16;
+        // small matrices: do not leave SMs idle behind a handful of fat super-batches
+        while (tn.warps_per_cta <= 0 && nw > 2 && (uint64_t)nw * rq * (uint64_t)g_rt.sm_count > a->rows) nw /= 2;
         RowParams p{};
         p.row_ptr = a->row_ptr;
         p.col_idx = a->col_idx;
@@ -327,38 +366,63 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         p.n = n;
         p.ldb = (uint32_t)b->ld;
         p.ldc = (uint32_t)c->ld;
-        // rows per TMA batch: enough entries per bulk copy to be efficient, small enough that the
-        // persistent CTAs stay a narrow front over the matrix
-        uint32_t rb;
-        if (tn.rows_per_batch > 0) {
-            rb = (uint32_t)tn.rows_per_batch;
-        } else {
-            const double target = (double)n * s <= 32.0 ? 2560.0 : 1024.0;
-            rb = (uint32_t)std::min<double>(4096.0, target / std::max(1.0, mean));
+        // rows per TMA slice: ~128 entries per bulk copy
+        uint32_t R;
+        if (tn.rows_per_slice > 0)
+            R = (uint32_t)tn.rows_per_slice;
+        else
+            R = (uint32_t)std::min<double>(256.0, std::max(1.0, 128.0 / std::max(1.0, mean)));
+        R = std::max(rq, R / rq * rq);
+        // rows per warp inside a super-batch: the dominant row stride of a stencil-like matrix (so the
+        // warps of a CTA sweep adjacent lines), else one slice
+        uint32_t P = R;
+        bool strided = false;
+        if (tn.rows_per_warp > 0) {
+            P = (uint32_t)tn.rows_per_warp;
+        } else if (a->row_stride >= 2 * R) {
+            P = a->row_stride;
+            // enough super-batches to keep every SM busy: P = stride / m keeps warps w and w+m adjacent
+            while (P % 2 == 0 && P / 2 >= 2 * R && a->rows / ((uint64_t)nw * P) < 4ull * g_rt.sm_count) P /= 2;
+            strided = a->rows / ((uint64_t)nw * P) >= (uint64_t)g_rt.sm_count;
+            if (!strided) P = R;
         }
-        rb = std::max(rows_per_pass, rb / rows_per_pass * rows_per_pass);
-        rb = (uint32_t)round_up(rb, 4);
-        p.rb = rb;
-        p.rows_per_warp = (uint32_t)round_up((rb + nw - 1) / nw, 32u / sh.G);
-        p.num_batches = (uint32_t)((a->rows + rb - 1) / rb);
-        const double want = std::min<double>((double)rb * (double)a->max_row_nnz,
-                                             std::max(2.0 * rb * mean, rb * mean + 1024.0));
-        p.cap = (uint32_t)pad4((uint64_t)std::min<double>(want, 12288.0)) + 4;
+        P = std::max(R, (P + R - 1) / R * R);
+        p.P = P;
+        p.R = R;
+        const uint64_t S = (uint64_t)nw * P;
+        p.num_super = (uint32_t)((a->rows + S - 1) / S);
+        uint32_t sync_rows = 0;
+        if (tn.sync_rows > 0)
+            sync_rows = (uint32_t)tn.sync_rows;
+        else if (tn.sync_rows == 0 && strided)
+            sync_rows = std::max(4u, rpp);
+        if (sync_rows) {
+            sync_rows = std::max(sync_rows, rpp) / rpp * rpp;
+            while (R % sync_rows) --sync_rows;   // terminates at a divisor (rpp divides R)
+            if (sync_rows % rpp) sync_rows = rpp;
+        }
+        p.sync_rows = sync_rows;
+        const double want = std::min<double>((double)R * (double)a->max_row_nnz, 2.0 * R * mean + 64.0);
+        p.cap = (uint32_t)pad4((uint64_t)std::min<double>(want, 4096.0)) + 4;
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
-        p.far_thr = (flags & BSM_TUNE_B_FAR_NOALLOC) ? (tn.far_threshold ? tn.far_threshold : 4096u) : 0u;
         p.flags = flags;
-        size_t smem = row_kernel_smem_bytes(a->dtype, p);
-        while (smem > (size_t)g_rt.max_smem_optin - 1024 && p.stages > 1) {
+        size_t smem = row_kernel_smem_bytes(a->dtype, p, nw);
+        const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
+        while (smem > smem_max && p.stages > 1) {
             --p.stages;
-            smem = row_kernel_smem_bytes(a->dtype, p);
+            smem = row_kernel_smem_bytes(a->dtype, p, nw);
         }
-        if (smem > (size_t)g_rt.max_smem_optin - 1024) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: batch does not fit shared memory");
-        const int block = (nw + 1) * 32;
+        while (smem > smem_max && p.cap > 8) {   // oversize slices take the global-memory path of the kernel
+            p.cap = (uint32_t)pad4(p.cap / 2);
+            smem = row_kernel_smem_bytes(a->dtype, p, nw);
+        }
+        if (smem > smem_max) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: slice ring does not fit shared memory");
+        const int block = nw * 32;
         int occ = 0;
-        BSM_TRY(row_kernel_occupancy(a->dtype, sh, block, smem, &occ));
+        BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, block, smem, &occ));
         if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_vector: kernel does not fit on an SM");
-        int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
-        const int grid = (int)std::min<uint64_t>(p.num_batches, (uint64_t)g_rt.sm_count * ctas);
+        int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 2);
+        const int grid = (int)std::min<uint64_t>(p.num_super, (uint64_t)g_rt.sm_count * ctas);
         if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, grid, block, smem, g_rt.stream));
         g_info.kernels += grid > 0;
         g_info.vec_elems = sh.V;
@@ -367,7 +431,9 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         g_info.grid = grid;
         g_info.block = block;
         g_info.smem_bytes = (int)smem;
-        g_info.rows_per_batch = (int)p.rb;
+        g_info.rows_per_slice = (int)p.R;
+        g_info.rows_per_warp = (int)p.P;
+        g_info.sync_rows = (int)p.sync_rows;
         g_info.stages = (int)p.stages;
         g_info.capacity = (int)p.cap;
     }

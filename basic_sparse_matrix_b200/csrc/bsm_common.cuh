@@ -60,6 +60,7 @@ struct bsm_csr {
     uint32_t *row_ptr = nullptr;   // u32[rows+1]
     bool owns = true;
     uint64_t max_row_nnz = 0;      // csr_row_stats (dispatch heuristic)
+    uint32_t row_stride = 0;       // dominant off-diagonal column stride of a stencil-like matrix (0 = none)
     // merge-path partition cache (depends only on A and the item count)
     int part_items = 0;
     uint32_t part_chunks = 0;

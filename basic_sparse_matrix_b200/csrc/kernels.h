@@ -22,16 +22,16 @@ struct RowParams {
     uint32_t rows;
     uint32_t n;      // columns in this pass
     uint32_t ldb, ldc;
-    uint32_t rb;     // rows per batch (multiple of 4)
-    uint32_t num_batches;
-    uint32_t cap;    // staged entries per stage (multiple of 4)
-    uint32_t stages;
-    uint32_t rows_per_warp;  // rows of a batch owned by one compute warp
-    uint32_t far_thr;        // 0 = off
-    uint32_t flags;          // BSM_TUNE_*
+    uint32_t P;          // consecutive rows owned by one warp inside a super-batch (multiple of R)
+    uint32_t R;          // rows per TMA slice of one warp (multiple of 4 and of 32/G)
+    uint32_t num_super;  // super-batches = ceil(rows / (warps * P))
+    uint32_t cap;        // staged entries per slice (multiple of 4)
+    uint32_t stages;     // TMA ring depth per warp
+    uint32_t sync_rows;  // CTA barrier every this many rows of a warp (0 = never; divides R)
+    uint32_t flags;      // BSM_TUNE_*
 };
-size_t row_kernel_smem_bytes(int dtype, const RowParams &p);
-int row_kernel_occupancy(int dtype, Shape sh, int block, size_t smem, int *blocks_per_sm);
+size_t row_kernel_smem_bytes(int dtype, const RowParams &p, int warps);
+int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int block, size_t smem, int *blocks_per_sm);
 int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int grid, int block, size_t smem,
                      cudaStream_t stream);
 

@@ -323,7 +323,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     barrier = (lambda: dist.barrier()) if world > 1 else None
     gpu.init(local)
-    gpu.set_stream(torch.cuda.current_stream().cuda_stream)
+    # the library enqueues on the stream it is given; torch.cuda.Event only sees torch's CURRENT
+    # stream, so the whole bench runs inside one dedicated non-default torch stream
+    stream = torch.cuda.Stream()
+    gpu.set_stream(stream.cuda_stream)
+    torch.cuda.set_stream(stream)
     peak, peak_src = load_peaks()
 
     kind, prm, n, dt = WORKLOADS[args.workload]

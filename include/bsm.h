@@ -62,22 +62,24 @@ typedef enum bsm_algo { BSM_ALGO_AUTO = 0, BSM_ALGO_VECTOR = 1, BSM_ALGO_MERGE =
 /* bsm_tuning.flags */
 #define BSM_TUNE_A_EVICT_FIRST 0x1u   /* L2 evict-first policy on the TMA bulk copies of col_idx/values */
 #define BSM_TUNE_C_STREAMING   0x2u   /* st.global.cs for C rows                                       */
-#define BSM_TUNE_B_FAR_NOALLOC 0x4u   /* ld.global.nc.L1::no_allocate for |col-row| > far_threshold     */
 #define BSM_TUNE_DEFAULT_FLAGS (BSM_TUNE_A_EVICT_FIRST | BSM_TUNE_C_STREAMING)
 
 /* Launch tuning; all-zero = library heuristics. Used by the bench sweeps and tests. */
 typedef struct bsm_tuning {
     int32_t algo;            /* bsm_algo                                                            */
-    int32_t col_tile;        /* columns per pass over A (0 = all n in one pass)                     */
-    int32_t rows_per_batch;  /* vector kernel: rows staged per TMA batch (0 = heuristic)            */
-    int32_t stages;          /* vector kernel: TMA pipeline depth (0 = heuristic)                   */
+    int32_t col_tile;        /* columns per pass over A (0 = heuristic, -1 = all n in one pass)     */
+    int32_t rows_per_slice;  /* vector kernel: rows of one warp staged per TMA slice (0 = heuristic)*/
+    int32_t stages;          /* vector kernel: TMA ring depth per warp (0 = heuristic)              */
     int32_t warps_per_cta;   /* compute warps per CTA (0 = heuristic)                               */
     int32_t ctas_per_sm;     /* persistent grid = SMs x this (0 = heuristic)                        */
     int32_t merge_items;     /* merge-path: (rows+nnz) items per lane group (0 = heuristic)         */
     uint32_t flags;          /* BSM_TUNE_* (0 = BSM_TUNE_DEFAULT_FLAGS); bit31 set = take literally */
-    uint32_t far_threshold;  /* for BSM_TUNE_B_FAR_NOALLOC                                          */
+    int32_t rows_per_warp;   /* vector kernel: consecutive rows a warp owns inside a CTA's
+                                super-batch (0 = heuristic: the matrix's dominant row stride)       */
     int32_t prefer_wide_rows;/* 1: full warp per row even when 128-bit loads need fewer lanes       */
-    int32_t reserved[6];
+    int32_t sync_rows;       /* vector kernel: CTA barrier every this many rows so that the warps of
+                                a CTA sweep neighbouring lines in step (0 = heuristic, -1 = never)  */
+    int32_t reserved[5];
 } bsm_tuning;
 
 /* what the last bsm_spmm* call on this thread actually launched */
@@ -89,10 +91,11 @@ typedef struct bsm_launch_info {
     int32_t reg_tiles;       /* NT                                                                  */
     int32_t grid, block;     /* of the main kernel                                                  */
     int32_t smem_bytes;
-    int32_t rows_per_batch, stages, capacity;
+    int32_t rows_per_slice, stages, capacity;
     int32_t passes;          /* column-tile passes                                                  */
     int32_t merge_items, merge_chunks;
-    int32_t reserved[4];
+    int32_t rows_per_warp, sync_rows, col_tile;
+    int32_t reserved[1];
 } bsm_launch_info;
 
 /* ------------------------------------------------------------------------------------------

@@ -253,11 +253,15 @@ class OracleCsr:
             raise RuntimeError(MATERR[rc])
         return out
 
-    def time_mul_dense_rows(self, rhs_columns, row_begin, row_end, faithful=True):
-        """Seconds for the faithful multiply of rows [row_begin,row_end) (CPU baseline leg)."""
+    def time_mul_dense_rows(self, rhs_columns, row_begin, row_end, faithful=True, rhs_row_count=None):
+        """Seconds for the faithful multiply of rows [row_begin,row_end) (CPU baseline leg).
+        ``rhs_row_count`` overrides the row count used by the dims check (sparse.rs:427-429) when the
+        columns passed are only the window of B that the sampled rows reference."""
         assert self._sfx in ("f32", "f64")
         ncols = len(rhs_columns)
         nrows = len(rhs_columns[0]) if ncols else 0
+        if rhs_row_count is not None:
+            nrows = int(rhs_row_count)
         arr, keep = _colptrs(rhs_columns, self._sfx)
         nnz = C.c_size_t(0)
         t = getattr(lib(), f"ocsr_time_mul_dense_rows_{self._sfx}")(

@@ -1,0 +1,36 @@
+// build.rs — compiles the hand-written sm_100a kernels with nvcc and links them into the crate.
+// No CPU fallback is built: without nvcc the build fails loudly.
+use std::{env, path::PathBuf, process::Command};
+
+fn main() {
+    let out = PathBuf::from(env::var("OUT_DIR").unwrap());
+    let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
+    let nvcc = format!("{cuda}/bin/nvcc");
+    let sources = ["bsm_api.cu", "spmm_rows.cu", "spmm_merge.cu", "convert.cu", "gen.cu", "bsm_nccl.cu"];
+    let mut objects = Vec::new();
+    for src in sources {
+        let obj = out.join(format!("{src}.o"));
+        let status = Command::new(&nvcc)
+            .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+                   "-Xcompiler", "-fPIC", "-c"])
+            .arg(format!("csrc/{src}"))
+            .arg("-o").arg(&obj)
+            .status()
+            .expect("nvcc not found: the gpu module has no CPU fallback");
+        assert!(status.success(), "nvcc failed on {src}");
+        println!("cargo:rerun-if-changed=csrc/{src}");
+        objects.push(obj);
+    }
+    let lib = out.join("libbsm_b200.a");
+    let status = Command::new("ar").arg("crs").arg(&lib).args(&objects).status().unwrap();
+    assert!(status.success());
+    println!("cargo:rustc-link-search=native={}", out.display());
+    println!("cargo:rustc-link-lib=static=bsm_b200");
+    println!("cargo:rustc-link-search=native={cuda}/lib64");
+    println!("cargo:rustc-link-lib=dylib=cudart");
+    println!("cargo:rustc-link-lib=dylib=nccl");
+    println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rerun-if-changed=csrc/bsm_common.cuh");
+    println!("cargo:rerun-if-changed=csrc/kernels.h");
+    println!("cargo:rerun-if-changed=csrc/bsm.h");
+}
