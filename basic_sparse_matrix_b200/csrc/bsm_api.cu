@@ -376,54 +376,61 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // rows per warp inside a super-batch: the dominant row stride of a stencil-like matrix (so the
         // warps of a CTA sweep adjacent lines), else one slice
         uint32_t P = R;
-        bool strided = false;
         if (tn.rows_per_warp > 0) {
             P = (uint32_t)tn.rows_per_warp;
         } else if (a->row_stride >= 2 * R) {
             P = a->row_stride;
             // enough super-batches to keep every SM busy: P = stride / m keeps warps w and w+m adjacent
             while (P % 2 == 0 && P / 2 >= 2 * R && a->rows / ((uint64_t)nw * P) < 4ull * g_rt.sm_count) P /= 2;
-            strided = a->rows / ((uint64_t)nw * P) >= (uint64_t)g_rt.sm_count;
-            if (!strided) P = R;
+            if (a->rows / ((uint64_t)nw * P) < (uint64_t)g_rt.sm_count) P = R;
         }
         P = std::max(R, (P + R - 1) / R * R);
         p.P = P;
         p.R = R;
+        // register-budget flavour (spmm_rows_inst.cuh); flavours 2 and 3 exist for full-width G == 32 shapes
+        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 4) - 1 : 0;
+        const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
+        if (!wide_full) flavour = 0;
+        if (flavour >= 2 && nw > 8) nw = 8;
         const uint64_t S = (uint64_t)nw * P;
         p.num_super = (uint32_t)((a->rows + S - 1) / S);
-        uint32_t sync_rows = 0;
-        if (tn.sync_rows > 0)
-            sync_rows = (uint32_t)tn.sync_rows;
-        else if (tn.sync_rows == 0 && strided)
-            sync_rows = std::max(4u, rpp);
-        if (sync_rows) {
-            sync_rows = std::max(sync_rows, rpp) / rpp * rpp;
-            while (R % sync_rows) --sync_rows;   // terminates at a divisor (rpp divides R)
-            if (sync_rows % rpp) sync_rows = rpp;
-        }
-        p.sync_rows = sync_rows;
-        const double want = std::min<double>((double)R * (double)a->max_row_nnz, 2.0 * R * mean + 64.0);
-        p.cap = (uint32_t)pad4((uint64_t)std::min<double>(want, 4096.0)) + 4;
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
         p.flags = flags;
-        size_t smem = row_kernel_smem_bytes(a->dtype, p, nw);
+        // the stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start);
+        // when even the smallest slice cannot fit, col_idx / values are read from global memory instead
         const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
+        auto cap_for = [&](uint32_t rows_per_slice) { return (uint32_t)pad4((uint64_t)rows_per_slice * a->max_row_nnz + 3) + 4; };
+        p.cap = cap_for(p.R);
+        size_t smem = row_kernel_smem_bytes(a->dtype, p, nw);
+        const size_t smem_soft = std::min<size_t>(smem_max, 112 * 1024);   // leave L1 room for the B rows
+        while (smem > smem_soft && p.stages > 2) {
+            --p.stages;
+            smem = row_kernel_smem_bytes(a->dtype, p, nw);
+        }
+        while (smem > smem_soft && p.R > rq && tn.rows_per_slice <= 0) {
+            p.R = std::max(rq, p.R / 2 / rq * rq);
+            p.P = std::max(p.R, p.P / p.R * p.R);
+            p.cap = cap_for(p.R);
+            smem = row_kernel_smem_bytes(a->dtype, p, nw);
+        }
         while (smem > smem_max && p.stages > 1) {
             --p.stages;
             smem = row_kernel_smem_bytes(a->dtype, p, nw);
         }
-        while (smem > smem_max && p.cap > 8) {   // oversize slices take the global-memory path of the kernel
-            p.cap = (uint32_t)pad4(p.cap / 2);
+        if (smem > smem_max) {   // rows too long to stage: unstaged variant (row_ptr windows only)
+            flavour = -1;
+            p.cap = 0;
+            p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
             smem = row_kernel_smem_bytes(a->dtype, p, nw);
         }
         if (smem > smem_max) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: slice ring does not fit shared memory");
         const int block = nw * 32;
         int occ = 0;
-        BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, block, smem, &occ));
+        BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, flavour, block, smem, &occ));
         if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_vector: kernel does not fit on an SM");
-        int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 2);
+        int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
         const int grid = (int)std::min<uint64_t>(p.num_super, (uint64_t)g_rt.sm_count * ctas);
-        if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, grid, block, smem, g_rt.stream));
+        if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, flavour, grid, block, smem, ctas, g_rt.stream));
         g_info.kernels += grid > 0;
         g_info.vec_elems = sh.V;
         g_info.lanes_per_row = sh.G;
@@ -433,7 +440,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         g_info.smem_bytes = (int)smem;
         g_info.rows_per_slice = (int)p.R;
         g_info.rows_per_warp = (int)p.P;
-        g_info.sync_rows = (int)p.sync_rows;
+        g_info.reg_flavour = flavour + 1;
         g_info.stages = (int)p.stages;
         g_info.capacity = (int)p.cap;
     }

@@ -27,13 +27,13 @@ struct RowParams {
     uint32_t num_super;  // super-batches = ceil(rows / (warps * P))
     uint32_t cap;        // staged entries per slice (multiple of 4)
     uint32_t stages;     // TMA ring depth per warp
-    uint32_t sync_rows;  // CTA barrier every this many rows of a warp (0 = never; divides R)
     uint32_t flags;      // BSM_TUNE_*
 };
 size_t row_kernel_smem_bytes(int dtype, const RowParams &p, int warps);
-int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int block, size_t smem, int *blocks_per_sm);
-int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int grid, int block, size_t smem,
-                     cudaStream_t stream);
+// flavour: register-budget variant of the kernel (0..3, -1 = unstaged), see spmm_rows_inst.cuh
+int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int flavour, int block, size_t smem, int *blocks_per_sm);
+int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int flavour, int grid, int block, size_t smem,
+                     int ctas_per_sm, cudaStream_t stream);
 
 // ---- merge-path kernel ---------------------------------------------------------------------
 struct MergeParams {

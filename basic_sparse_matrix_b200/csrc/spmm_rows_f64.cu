@@ -1,0 +1,11 @@
+// spmm_rows_f64.cu — f64 instantiations of the vector-CSR kernel (see spmm_rows_kernel.cuh).
+#include "spmm_rows_inst.cuh"
+
+namespace bsm {
+const void *row_kernel_select_f64(Shape sh, bool fulln, int flavour)
+{
+    if (sh.V == 1) return row_kernel_select_v<double, 1>(sh, fulln, flavour);
+    if (sh.V == 2) return row_kernel_select_v<double, 2>(sh, fulln, flavour);
+    return nullptr;
+}
+}  // namespace bsm

@@ -1,0 +1,67 @@
+// spmm_rows_inst.cuh — instantiation table of spmm_rows_kernel for one element type (included by
+// spmm_rows_f64.cu / spmm_rows_f32.cu so the two compile in parallel).
+#pragma once
+#include "spmm_rows_kernel.cuh"
+
+namespace bsm {
+
+constexpr int row_default_u(int NT) { return NT >= 4 ? 2 : (NT == 2 ? 4 : 8); }
+
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true> static const void *rk()
+{
+    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED>);
+}
+
+// Register-budget flavours (`flavour` argument of the selectors):
+//   0: CTAs of up to 512 threads, 1 per SM (<= 128 registers)       — the default
+//   1: same, gather window twice as deep
+//   2: CTAs of up to 256 threads, 3 per SM (<= 85 registers)
+//   3: CTAs of up to 256 threads, 4 per SM (<= 64 registers)
+//  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
+// G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
+template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int flavour)
+{
+    constexpr int U1 = row_default_u(NT), U2 = 2 * U1;
+    if (flavour < 0) return fulln ? rk<T, V, 32, NT, true, U1, 512, 1, false>() : rk<T, V, 32, NT, false, U1, 512, 1, false>();
+    if (fulln) {
+        switch (flavour) {
+            case 1: return rk<T, V, 32, NT, true, U2, 512, 1>();
+            case 2: return rk<T, V, 32, NT, true, U1, 256, 3>();
+            case 3: return rk<T, V, 32, NT, true, U1, 256, 4>();
+        }
+        return rk<T, V, 32, NT, true, U1, 512, 1>();
+    }
+    return rk<T, V, 32, NT, false, U1, 512, 1>();
+}
+
+template <typename T, int V, int G> static const void *rk_narrow(bool fulln, int flavour)
+{
+    if (flavour < 0) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, false>() : rk<T, V, G, 1, false, 8, 512, 1, false>();
+    return fulln ? rk<T, V, G, 1, true, 8, 512, 1>() : rk<T, V, G, 1, false, 8, 512, 1>();
+}
+
+template <typename T, int V> static const void *row_kernel_select_v(Shape sh, bool fulln, int flavour)
+{
+    if (sh.G == 32) {
+        switch (sh.NT) {
+            case 1: return rk_wide<T, V, 1>(fulln, flavour);
+            case 2: return rk_wide<T, V, 2>(fulln, flavour);
+            case 4: return rk_wide<T, V, 4>(fulln, flavour);
+        }
+        return nullptr;
+    }
+    if (sh.NT != 1) return nullptr;
+    switch (sh.G) {
+        case 16: return rk_narrow<T, V, 16>(fulln, flavour);
+        case 8: return rk_narrow<T, V, 8>(fulln, flavour);
+        case 4: return rk_narrow<T, V, 4>(fulln, flavour);
+        case 2: return rk_narrow<T, V, 2>(fulln, flavour);
+        case 1: return rk_narrow<T, V, 1>(fulln, flavour);
+    }
+    return nullptr;
+}
+
+// largest CTA (threads) a flavour was compiled for
+inline int row_flavour_max_threads(int flavour) { return flavour >= 2 ? 256 : 512; }
+
+}  // namespace bsm

@@ -1,0 +1,272 @@
+// spmm_rows_kernel.cuh — vector-CSR SpMM/SpMV for short and regular rows (sm_100a).
+//
+// Replaces the loop nest of Csr::mul_dense, /root/reference/src/sparse.rs:431-444:
+//     for row { row = get_row_compact(row); for out_col { value = 0;
+//         for entry in row (stored order) { value = value + entry.v * B[entry.col][out_col] } } }
+//
+// Design (B200):
+//   * persistent CTAs of W warps. A CTA owns "super-batches" of W*P consecutive rows
+//     (blockIdx, +grid, ...); inside one, warp w owns the P consecutive rows [w*P, (w+1)*P) and
+//     walks them in slices of R rows. With P = one grid line of a stencil matrix the W warps of a
+//     CTA sweep W adjacent lines side by side, so the +-1-line neighbours of B are L1 hits, not
+//     L2 traffic (optionally kept in step by a CTA barrier every few rows);
+//   * every warp is its own TMA pipeline: lane 0 streams the slice's contiguous piece of
+//     col_idx / values and its row_ptr window into a warp-private shared-memory ring with bulk
+//     copies (cp.async.bulk -> UBLKCP) that complete on per-stage mbarriers, `stages-1` slices
+//     ahead of the slice being consumed. The A stream never occupies registers or L1;
+//   * a group of G lanes owns one output row; every lane owns V consecutive columns per register
+//     tile (V*sizeof(T) up to 16 bytes -> 128-bit coalesced B-row loads on the read-only path).
+//     G == 32: the warp treats its slice as ONE flat entry stream — U B-row gathers are always in
+//     flight, whatever the row lengths — and closes a row (one streaming store of C) whenever the
+//     stream crosses a row end. G < 32: 32/G rows side by side, row by row;
+//   * entries are consumed IN STORED ORDER with a separately rounded multiply and add
+//     -> bit-identical to the reference's sequential sum for any input.
+//
+// A slice whose entry count exceeds the stage capacity (irregular matrices forced onto this
+// kernel) reads col_idx/values straight from global memory — same arithmetic.
+#pragma once
+#include "bsm_common.cuh"
+#include "kernels.h"
+
+namespace bsm {
+
+constexpr int kMaxStages = 8;
+
+struct RowSmemLayout {
+    uint32_t vals_off, idx_off, rp_off, stage_bytes;
+};
+__host__ __device__ inline RowSmemLayout row_layout(uint32_t cap, uint32_t R, uint32_t tsize)
+{
+    RowSmemLayout l;
+    l.vals_off = 0;
+    l.idx_off = cap * tsize;                  // cap % 4 == 0 -> 16-byte aligned
+    l.rp_off = l.idx_off + cap * 4;
+    l.stage_bytes = l.rp_off + (R + 4) * 4;   // R % 4 == 0
+    return l;
+}
+
+// B row `c` of this lane: b_bytes already points at the lane's first column
+template <typename T, int V, int NT, bool FULLN>
+__device__ __forceinline__ void load_brow(Lane<T, V> (&b)[NT], const char *__restrict__ b_bytes, uint32_t ldb_bytes, uint32_t c,
+                                          const bool (&col_ok)[NT], int G)
+{
+    const T *brow = reinterpret_cast<const T *>(b_bytes + (size_t)c * ldb_bytes);   // one IMAD.WIDE
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+        if (FULLN || col_ok[t]) b[t].load(brow + t * G * V, false);
+}
+
+template <typename T, int V, int NT>
+__device__ __forceinline__ void fma_row(Lane<T, V> (&acc)[NT], const Lane<T, V> (&b)[NT], T a)
+{
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[t].x[i] = mul_add<false>(a, b[t].x[i], acc[t].x[i]);   // sparse.rs:438-439
+}
+
+// One slice of one warp: rows [row0, row0+nr), entry k of the matrix at ci[k - base] / va[k - base]
+// (shared memory when the slice was staged by TMA, else the global arrays with base = 0).
+template <typename T, int V, int G, int NT, bool FULLN, int U>
+__device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t *__restrict__ rp, const uint32_t *__restrict__ ci,
+                                              const T *__restrict__ va, uint32_t base, uint32_t row0, uint32_t nr,
+                                              const char *__restrict__ b_bytes, char *__restrict__ c_bytes, const bool (&col_ok)[NT],
+                                              uint32_t grp, bool streaming)
+{
+    constexpr int RPP = 32 / G;
+    const uint32_t ldb_bytes = p.ldb * (uint32_t)sizeof(T);
+    const uint32_t ldc_bytes = p.ldc * (uint32_t)sizeof(T);
+    ci -= base;   // entry k at ci[k] / va[k]
+    va -= base;
+    if constexpr (G == 32) {
+        // ======== one flat entry stream per warp ========
+        const uint32_t s_all = rp[0], e_all = rp[nr];
+        Lane<T, V> acc[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t].zero();                   // T::default()  sparse.rs:434
+        uint32_t rr = 0;                                               // row being accumulated (slice-local)
+        uint32_t row_end = rp[1];
+        char *crow = c_bytes + (size_t)row0 * ldc_bytes;
+        auto close_row = [&]() {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                if (FULLN || col_ok[t]) acc[t].store(reinterpret_cast<T *>(crow) + t * G * V, streaming);
+                acc[t].zero();
+            }
+            crow += ldc_bytes;
+            ++rr;
+            row_end = rp[min(rr + 1u, nr)];
+        };
+        // rolling window of U gathers: slot u holds entry k+u until it is consumed and is then
+        // refilled with entry k+u+U at once, so U gathers stay in flight whatever the row lengths
+        // (the prologue loads every slot unconditionally — past the end it re-reads the last entry —
+        // so that no slot starts life as a predicated, partially defined register)
+        Lane<T, V> b[U][NT];
+        if (s_all < e_all) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[min(s_all + u, e_all - 1u)], col_ok, G);
+        }
+        uint32_t k = s_all;
+        for (; k + 2 * U <= e_all; k += U) {   // steady state: no bounds checks
+#pragma unroll
+            for (int u = 0; u < U; ++u) {      // consumed strictly in stored order
+                while (k + u == row_end) close_row();
+                fma_row<T, V, NT>(acc, b[u], va[k + u]);
+                load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
+            }
+        }
+        for (; k < e_all; k += U) {            // drain
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k + u < e_all) {
+                    while (k + u == row_end) close_row();
+                    fma_row<T, V, NT>(acc, b[u], va[k + u]);
+                    if (k + u + U < e_all) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
+                }
+            }
+        }
+        while (rr < nr) close_row();   // the last row with entries, then trailing empty rows
+    } else {
+        // ======== 32/G rows side by side, row by row ========
+        for (uint32_t r = grp; r < nr; r += RPP) {
+            const uint32_t s = rp[r], e = rp[r + 1];
+            Lane<T, V> acc[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t].zero();
+            Lane<T, V> b[U][NT];
+            if (s < e) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[min(s + u, e - 1u)], col_ok, G);
+            }
+            uint32_t k = s;
+            for (; k + 2 * U <= e; k += U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    fma_row<T, V, NT>(acc, b[u], va[k + u]);
+                    load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
+                }
+            }
+            for (; k < e; k += U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (k + u < e) {
+                        fma_row<T, V, NT>(acc, b[u], va[k + u]);
+                        if (k + u + U < e) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
+                    }
+                }
+            }
+            T *crow = reinterpret_cast<T *>(c_bytes + (size_t)(row0 + r) * ldc_bytes);
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+                if (FULLN || col_ok[t]) acc[t].store(crow + t * G * V, streaming);
+        }
+    }
+}
+
+// U = B-row gathers kept in flight per lane group (a rolling window: entry k+U is requested as soon
+// as entry k has been consumed); MAXT / MINB = launch bounds (threads per CTA, CTAs per SM the register allocation must allow).
+// STAGED = col_idx / values of every slice fit the TMA stage (the host guarantees it from the longest
+// row); the unstaged variant reads them from global memory and stages only the row_ptr windows.
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED>
+__global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t W = blockDim.x >> 5;
+    const RowSmemLayout L = row_layout(p.cap, p.R, sizeof(T));
+    unsigned char *ring = smem + (size_t)warp * p.stages * L.stage_bytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)W * p.stages * L.stage_bytes) + warp * p.stages;
+
+    if (lane == 0) {
+        for (uint32_t s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const T *__restrict__ vals = static_cast<const T *>(p.vals);
+    const uint32_t S = W * p.P;                 // rows per super-batch
+    const uint32_t spw = p.P / p.R;             // slices per warp per super-batch
+    const uint32_t my_supers = blockIdx.x < p.num_super ? (p.num_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t my_slices = my_supers * spw;
+
+    // first row of this warp's i-th slice
+    auto slice_row0 = [&](uint32_t i) -> uint64_t {
+        const uint32_t k = i / spw, t = i - k * spw;
+        return (uint64_t)(blockIdx.x + k * gridDim.x) * S + (uint64_t)warp * p.P + (uint64_t)t * p.R;
+    };
+
+    // ---- producer side (lane 0): TMA bulk copies of one slice into ring stage i % stages --------
+    const uint64_t policy = (p.flags & BSM_TUNE_A_EVICT_FIRST) ? l2_policy_evict_first() : l2_policy_evict_normal();
+    uint32_t pf_s = 0, pf_e = 0;                // entry range of the next slice to issue (prefetched)
+    auto prefetch_bounds = [&](uint32_t i) {
+        if (i < my_slices) {
+            const uint64_t r0 = slice_row0(i);
+            if (r0 < p.rows) {
+                const uint32_t r1 = (uint32_t)min(r0 + p.R, (uint64_t)p.rows);
+                pf_s = __ldg(p.row_ptr + r0);
+                pf_e = __ldg(p.row_ptr + r1);
+            }
+        }
+    };
+    auto issue = [&](uint32_t i) {
+        // only lane 0 calls this
+        const uint64_t r0 = slice_row0(i);
+        if (r0 < p.rows) {
+            const uint32_t nr = (uint32_t)min((uint64_t)p.R, p.rows - r0);
+            const uint32_t stage = i % p.stages;
+            unsigned char *st = ring + (size_t)stage * L.stage_bytes;
+            const uint32_t base = pf_s & ~3u;                     // 16-byte aligned start for u32 and T
+            const uint32_t cnt = STAGED ? ((pf_e - base + 3u) & ~3u) : 0u;   // entries, multiple of 4
+            if (STAGED && cnt > p.cap) __trap();   // the host sizes cap from the longest row; never overrun the stage
+            const uint32_t cnt_r = (nr + 1u + 3u) & ~3u;          // row_ptr window rp[r0 .. r0+nr]
+            mbar_arrive_expect_tx(&full_bar[stage], cnt_r * 4u + cnt * (4u + (uint32_t)sizeof(T)));
+            bulk_g2s(st + L.rp_off, p.row_ptr + r0, cnt_r * 4u, &full_bar[stage], policy);
+            if (cnt) {
+                bulk_g2s(st + L.idx_off, p.col_idx + base, cnt * 4u, &full_bar[stage], policy);
+                bulk_g2s(st + L.vals_off, vals + base, cnt * (uint32_t)sizeof(T), &full_bar[stage], policy);
+            }
+        }
+        prefetch_bounds(i + 1);
+    };
+
+    if (lane == 0) {
+        prefetch_bounds(0);
+        for (uint32_t i = 0; i + 1 < p.stages && i < my_slices; ++i) issue(i);
+    }
+
+    // ---- consumer side -------------------------------------------------------------------------
+    const uint32_t grp = lane / G;    // which of the warp's concurrent rows (G < 32)
+    const uint32_t gl = lane % G;     // lane inside the group
+    bool col_ok[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) col_ok[t] = FULLN || (uint32_t)((t * G + gl) * V) < p.n;
+    const char *__restrict__ b_bytes = reinterpret_cast<const char *>(static_cast<const T *>(p.B) + gl * V);
+    char *__restrict__ c_bytes = reinterpret_cast<char *>(static_cast<T *>(p.C) + gl * V);
+    const bool streaming = (p.flags & BSM_TUNE_C_STREAMING) != 0;
+
+    for (uint32_t i = 0; i < my_slices; ++i) {
+        __syncwarp();   // every lane is done reading the stage that is refilled next
+        if (lane == 0 && i + p.stages - 1 < my_slices) issue(i + p.stages - 1);
+
+        const uint64_t row0_64 = slice_row0(i);
+        if (row0_64 < p.rows) {
+            const uint32_t row0 = (uint32_t)row0_64;
+            const uint32_t nr = min(p.R, p.rows - row0);
+            const uint32_t stage = i % p.stages;
+            mbar_wait(&full_bar[stage], (i / p.stages) & 1u);   // TMA bytes of this slice have landed
+
+            const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
+            if constexpr (STAGED)
+                process_slice<T, V, G, NT, FULLN, U>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
+                                                     reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes, c_bytes,
+                                                     col_ok, grp, streaming);
+            else
+                process_slice<T, V, G, NT, FULLN, U>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, streaming);
+        }
+    }
+}
+
+}  // namespace bsm

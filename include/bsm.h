@@ -77,8 +77,9 @@ typedef struct bsm_tuning {
     int32_t rows_per_warp;   /* vector kernel: consecutive rows a warp owns inside a CTA's
                                 super-batch (0 = heuristic: the matrix's dominant row stride)       */
     int32_t prefer_wide_rows;/* 1: full warp per row even when 128-bit loads need fewer lanes       */
-    int32_t sync_rows;       /* vector kernel: CTA barrier every this many rows so that the warps of
-                                a CTA sweep neighbouring lines in step (0 = heuristic, -1 = never)  */
+    int32_t reg_flavour;     /* vector kernel: register-budget variant. 0 = heuristic; 1 = CTAs of <= 512
+                                threads, 1 per SM; 2 = same with a gather window twice as deep;
+                                3 = CTAs of <= 256 threads, 3 per SM; 4 = <= 256 threads, 4 per SM  */
     int32_t reserved[5];
 } bsm_tuning;
 
@@ -91,10 +92,10 @@ typedef struct bsm_launch_info {
     int32_t reg_tiles;       /* NT                                                                  */
     int32_t grid, block;     /* of the main kernel                                                  */
     int32_t smem_bytes;
-    int32_t rows_per_slice, stages, capacity;
+    int32_t rows_per_slice, stages, capacity;   /* capacity 0 = col_idx/values not staged */
     int32_t passes;          /* column-tile passes                                                  */
     int32_t merge_items, merge_chunks;
-    int32_t rows_per_warp, sync_rows, col_tile;
+    int32_t rows_per_warp, reg_flavour, col_tile;
     int32_t reserved[1];
 } bsm_launch_info;
 

@@ -117,9 +117,9 @@ def test_vector_tuning_variants_are_bitwise_identical(gpu, dtype):
     for tune in (dict(rows_per_slice=8), dict(rows_per_slice=64, stages=2), dict(rows_per_slice=256, stages=1),
                  dict(col_tile=16), dict(col_tile=32, ctas_per_sm=1), dict(prefer_wide_rows=1),
                  dict(warps_per_cta=2), dict(warps_per_cta=16, ctas_per_sm=1), dict(flags=_lib.TUNE_LITERAL),
-                 dict(rows_per_warp=64, rows_per_slice=16, sync_rows=4), dict(rows_per_warp=96, rows_per_slice=8, sync_rows=8),
-                 dict(rows_per_warp=32, rows_per_slice=32, sync_rows=32, warps_per_cta=4),
-                 dict(rows_per_warp=512, rows_per_slice=4, sync_rows=2, stages=4), dict(sync_rows=-1, stages=8)):
+                 dict(rows_per_warp=64, rows_per_slice=16), dict(rows_per_warp=96, rows_per_slice=8, reg_flavour=2),
+                 dict(rows_per_warp=32, rows_per_slice=32, warps_per_cta=4, reg_flavour=3),
+                 dict(rows_per_warp=512, rows_per_slice=4, stages=4, reg_flavour=4), dict(reg_flavour=1, stages=8)):
         got, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", **tune)
         assert_bitwise(got, want, f"tuning {tune}")
 
