@@ -366,13 +366,56 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         p.n = n;
         p.ldb = (uint32_t)b->ld;
         p.ldc = (uint32_t)c->ld;
-        // rows per TMA slice: ~128 entries per bulk copy
+        // rows per TMA slice: ~128 entries per bulk copy; narrow shapes (32/G rows side by side) want
+        // several passes per slice to amortise the per-slice bookkeeping
+        const bool user_R = tn.rows_per_slice > 0, user_nw = tn.warps_per_cta > 0;
         uint32_t R;
-        if (tn.rows_per_slice > 0)
+        if (user_R) {
             R = (uint32_t)tn.rows_per_slice;
-        else
+        } else {
             R = (uint32_t)std::min<double>(256.0, std::max(1.0, 128.0 / std::max(1.0, mean)));
+            if (sh.G < 32) R = std::max(R, 4u * rpp);
+        }
         R = std::max(rq, R / rq * rq);
+        // register-budget flavour (spmm_rows_inst.cuh); flavours 2 and 3 exist for full-width G == 32 shapes
+        const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
+        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 4) - 1 : (wide_full && !user_nw ? 2 : 0);
+        if (!wide_full) flavour = 0;
+        if (flavour >= 2 && nw > 8) nw = 8;
+        p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
+        p.flags = flags;
+        p.prefetch = tn.prefetch_dist > 0 ? (uint32_t)tn.prefetch_dist : (tn.prefetch_dist < 0 ? 0u : 32u);
+        if (((size_t)n * s) % 16 == 0 && ((size_t)b->ld * s) % 16 == 0 && ((uintptr_t)bp % 16) == 0) p.flags |= 0x10000u;   // kRowFlagBulkPrefetch
+        // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start).
+        // Shrink, in this order, the ring depth, the slice and the CTA until the rings fit: first under
+        // a soft limit that leaves most of the 228 KB to L1 (where wide B rows live), then under the
+        // hardware limit. If even the smallest slice cannot be staged, col_idx / values are read from
+        // global memory instead (unstaged variant).
+        const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
+        const int resident = flavour == 2 ? 3 : (flavour == 3 ? 4 : 1);
+        const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (112 * 1024) / resident);
+        p.R = R;
+        auto smem_now = [&]() {
+            p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 4;
+            return row_kernel_smem_bytes(a->dtype, p, nw);
+        };
+        const uint32_t r_floor = sh.G < 32 ? std::max(rq, 2u * rpp) : rq;
+        size_t smem = smem_now();
+        const bool user_stages = tn.stages > 0;
+        while (smem > smem_soft && p.stages > 2 && !user_stages) { --p.stages; smem = smem_now(); }
+        while (smem > smem_soft && p.R > r_floor && !user_R) { p.R = std::max(r_floor, p.R / 2 / rq * rq); smem = smem_now(); }
+        while (smem > smem_soft && nw > 8 && !user_nw) { nw /= 2; smem = smem_now(); }
+        while (smem > smem_max && p.stages > 1) { --p.stages; smem = smem_now(); }
+        while (smem > smem_max && p.R > rq && !user_R) { p.R = std::max(rq, p.R / 2 / rq * rq); smem = smem_now(); }
+        while (smem > smem_max && nw > 2 && !user_nw) { nw /= 2; smem = smem_now(); }
+        if (smem > smem_max) {   // rows too long to stage: unstaged variant (row_ptr windows only)
+            flavour = -1;
+            p.cap = 0;
+            p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
+            smem = row_kernel_smem_bytes(a->dtype, p, nw);
+        }
+        if (smem > smem_max) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: slice ring does not fit shared memory");
+        R = p.R;
         // rows per warp inside a super-batch: the dominant row stride of a stencil-like matrix (so the
         // warps of a CTA sweep adjacent lines), else one slice
         uint32_t P = R;
@@ -386,44 +429,8 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         }
         P = std::max(R, (P + R - 1) / R * R);
         p.P = P;
-        p.R = R;
-        // register-budget flavour (spmm_rows_inst.cuh); flavours 2 and 3 exist for full-width G == 32 shapes
-        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 4) - 1 : 0;
-        const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
-        if (!wide_full) flavour = 0;
-        if (flavour >= 2 && nw > 8) nw = 8;
         const uint64_t S = (uint64_t)nw * P;
         p.num_super = (uint32_t)((a->rows + S - 1) / S);
-        p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
-        p.flags = flags;
-        // the stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start);
-        // when even the smallest slice cannot fit, col_idx / values are read from global memory instead
-        const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
-        auto cap_for = [&](uint32_t rows_per_slice) { return (uint32_t)pad4((uint64_t)rows_per_slice * a->max_row_nnz + 3) + 4; };
-        p.cap = cap_for(p.R);
-        size_t smem = row_kernel_smem_bytes(a->dtype, p, nw);
-        const size_t smem_soft = std::min<size_t>(smem_max, 112 * 1024);   // leave L1 room for the B rows
-        while (smem > smem_soft && p.stages > 2) {
-            --p.stages;
-            smem = row_kernel_smem_bytes(a->dtype, p, nw);
-        }
-        while (smem > smem_soft && p.R > rq && tn.rows_per_slice <= 0) {
-            p.R = std::max(rq, p.R / 2 / rq * rq);
-            p.P = std::max(p.R, p.P / p.R * p.R);
-            p.cap = cap_for(p.R);
-            smem = row_kernel_smem_bytes(a->dtype, p, nw);
-        }
-        while (smem > smem_max && p.stages > 1) {
-            --p.stages;
-            smem = row_kernel_smem_bytes(a->dtype, p, nw);
-        }
-        if (smem > smem_max) {   // rows too long to stage: unstaged variant (row_ptr windows only)
-            flavour = -1;
-            p.cap = 0;
-            p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
-            smem = row_kernel_smem_bytes(a->dtype, p, nw);
-        }
-        if (smem > smem_max) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: slice ring does not fit shared memory");
         const int block = nw * 32;
         int occ = 0;
         BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, flavour, block, smem, &occ));
@@ -443,6 +450,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         g_info.reg_flavour = flavour + 1;
         g_info.stages = (int)p.stages;
         g_info.capacity = (int)p.cap;
+        g_info.prefetch_dist = (sh.G == 32 && flavour >= 0) ? (int)p.prefetch : 0;
     }
     g_info.passes = passes;
     return BSM_OK;

@@ -77,9 +77,7 @@ def main():
             line = {"point": pt, "ms": round(total_ms / args.steps, 4), "ms_best": round(min(per), 4),
                     "gflops": round(2.0 * ai["nnz"] * n / t / 1e9, 1), "eff_gbs": round(bm / t / 1e9, 1),
                     "frac": round(bm / t / 1e9 / peak, 4), "same_as_first": bool(np.array_equal(got.view(np.uint8), ref.view(np.uint8))),
-                    "launch": {k: info[k] for k in ("algo", "vec_elems", "lanes_per_row", "reg_tiles", "grid", "block", "smem_bytes",
-                                                    "rows_per_slice", "rows_per_warp", "sync_rows", "stages", "capacity", "passes",
-                                                    "col_tile", "merge_items")}}
+                    "launch": info}
             lines.append(line)
             print(json.dumps(line), flush=True)
     if args.out:
