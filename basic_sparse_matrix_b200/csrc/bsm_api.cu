@@ -384,8 +384,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         if (flavour >= 2 && nw > 8) nw = 8;
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
         p.flags = flags;
-        p.prefetch = tn.prefetch_dist > 0 ? (uint32_t)tn.prefetch_dist : (tn.prefetch_dist < 0 ? 0u : 32u);
-        if (((size_t)n * s) % 16 == 0 && ((size_t)b->ld * s) % 16 == 0 && ((uintptr_t)bp % 16) == 0) p.flags |= 0x10000u;   // kRowFlagBulkPrefetch
         // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start).
         // Shrink, in this order, the ring depth, the slice and the CTA until the rings fit: first under
         // a soft limit that leaves most of the 228 KB to L1 (where wide B rows live), then under the
@@ -450,7 +448,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         g_info.reg_flavour = flavour + 1;
         g_info.stages = (int)p.stages;
         g_info.capacity = (int)p.cap;
-        g_info.prefetch_dist = (sh.G == 32 && flavour >= 0) ? (int)p.prefetch : 0;
     }
     g_info.passes = passes;
     return BSM_OK;

@@ -27,8 +27,7 @@ struct RowParams {
     uint32_t num_super;  // super-batches = ceil(rows / (warps * P))
     uint32_t cap;        // staged entries per slice (multiple of 4)
     uint32_t stages;     // TMA ring depth per warp
-    uint32_t prefetch;   // > 0: L2 prefetch of far B rows this many entries ahead of the gather window
-    uint32_t flags;      // BSM_TUNE_* (+ internal bits)
+    uint32_t flags;      // BSM_TUNE_*
 };
 size_t row_kernel_smem_bytes(int dtype, const RowParams &p, int warps);
 // flavour: register-budget variant of the kernel (0..3, -1 = unstaged), see spmm_rows_inst.cuh

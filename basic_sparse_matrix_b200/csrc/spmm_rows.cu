@@ -26,6 +26,8 @@ int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int flavour, int block
     const void *k = row_kernel_select(dtype, sh, n, flavour);
     if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rows: no kernel for this lane shape");
     BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // query under the largest carve-out (launch_spmm_rows narrows it to what the chosen residency needs)
+    BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     BSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, block, smem));
     return BSM_OK;
 }

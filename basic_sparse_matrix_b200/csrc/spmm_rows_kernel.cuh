@@ -31,7 +31,6 @@
 namespace bsm {
 
 constexpr int kMaxStages = 8;
-constexpr uint32_t kRowFlagBulkPrefetch = 0x10000u;   // RowParams.flags, internal: B row segments are 16-byte granular
 
 struct RowSmemLayout {
     uint32_t vals_off, idx_off, rp_off, stage_bytes;
@@ -45,30 +44,6 @@ __host__ __device__ inline RowSmemLayout row_layout(uint32_t cap, uint32_t R, ui
     l.stage_bytes = l.rp_off + (R + 4) * 4;   // R % 4 == 0
     return l;
 }
-
-// L2 prefetch of one B row segment (fire and forget): a TMA bulk prefetch when the segment is
-// 16-byte granular, else one prefetch per 128-byte line
-__device__ __forceinline__ void prefetch_brow_l2(const char *row, uint32_t bytes, bool bulk)
-{
-    if (bulk) {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(bytes) : "memory");
-    } else {
-        for (uint32_t off = 0; off < bytes; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
-    }
-}
-
-// What the L2 prefetcher of a slice needs: where B starts, which columns are "far" (outside the row
-// range the CTA's own warps sweep, i.e. not served by L1), and the next slice's staged col_idx.
-struct SlicePrefetch {
-    const char *b_base;        // first column of this pass, lane-independent
-    uint32_t row_bytes;        // n * sizeof(T)
-    bool bulk;
-    uint32_t near_lo, near_hi; // columns in [near_lo, near_hi) are left to L1
-    const uint32_t *ci_next;   // entry t of the next slice at ci_next[t]
-    uint32_t s_next, e_next;   // its entry range (empty when it has not landed yet)
-    uint32_t lane;
-    uint32_t dist;             // entries ahead; 0 = prefetch off
-};
 
 // B row `c` of this lane: b_bytes already points at the lane's first column
 template <typename T, int V, int NT, bool FULLN>
@@ -92,13 +67,11 @@ __device__ __forceinline__ void fma_row(Lane<T, V> (&acc)[NT], const Lane<T, V> 
 
 // One slice of one warp: rows [row0, row0+nr), entry k of the matrix at ci[k - base] / va[k - base]
 // (shared memory when the slice was staged by TMA, else the global arrays with base = 0).
-// pf.dist > 0: while entry k is consumed, the B row of entry k+dist (far columns only) is prefetched into L2,
-// so that by the time the gather window reaches it the load is an L2 hit, not a DRAM round trip.
 template <typename T, int V, int G, int NT, bool FULLN, int U>
 __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t *__restrict__ rp, const uint32_t *__restrict__ ci,
                                               const T *__restrict__ va, uint32_t base, uint32_t row0, uint32_t nr,
                                               const char *__restrict__ b_bytes, char *__restrict__ c_bytes, const bool (&col_ok)[NT],
-                                              uint32_t grp, bool streaming, const SlicePrefetch &pf)
+                                              uint32_t grp, bool streaming)
 {
     constexpr int RPP = 32 / G;
     const uint32_t ldb_bytes = p.ldb * (uint32_t)sizeof(T);
@@ -133,23 +106,8 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
 #pragma unroll
             for (int u = 0; u < U; ++u) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[min(s_all + u, e_all - 1u)], col_ok, G);
         }
-        auto prefetch_ahead = [&](uint32_t kk) {   // lanes 0..U-1: one entry each, PF entries ahead
-            if (pf.dist && pf.lane < (uint32_t)U) {
-                const uint32_t t = kk + pf.dist + pf.lane;
-                uint32_t c = 0xFFFFFFFFu;
-                if (t < e_all) {
-                    c = ci[t];
-                } else {
-                    const uint32_t t2 = pf.s_next + (t - e_all);
-                    if (t2 < pf.e_next) c = pf.ci_next[t2];
-                }
-                if (c != 0xFFFFFFFFu && (c < pf.near_lo || c >= pf.near_hi))
-                    prefetch_brow_l2(pf.b_base + (size_t)c * ldb_bytes, pf.row_bytes, pf.bulk);
-            }
-        };
         uint32_t k = s_all;
         for (; k + 2 * U <= e_all; k += U) {   // steady state: no bounds checks
-            prefetch_ahead(k);
 #pragma unroll
             for (int u = 0; u < U; ++u) {      // consumed strictly in stored order
                 while (k + u == row_end) close_row();
@@ -158,7 +116,6 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             }
         }
         for (; k < e_all; k += U) {            // drain
-            prefetch_ahead(k);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (k + u < e_all) {
@@ -302,37 +259,12 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
 
             const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
             const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
-            SlicePrefetch pf{};
-            pf.lane = lane;
-            if constexpr (STAGED && G == 32) {
-                if (p.prefetch) {
-                    pf.dist = p.prefetch;
-                    pf.b_base = static_cast<const char *>(p.B);
-                    pf.row_bytes = p.n * (uint32_t)sizeof(T);
-                    pf.bulk = (p.flags & kRowFlagBulkPrefetch) != 0;
-                    // columns inside the row range swept by this CTA's warps (+- one warp's worth) come from L1
-                    const uint64_t sb0 = (uint64_t)(blockIdx.x + (i / spw) * gridDim.x) * S;
-                    pf.near_lo = (uint32_t)(sb0 > p.P ? sb0 - p.P : 0);
-                    pf.near_hi = (uint32_t)min(sb0 + S + p.P, (uint64_t)0xFFFFFFFFu);
-                    if (i + 1 < my_slices && p.stages > 1) {   // the next slice's col_idx, if it has landed
-                        const uint64_t nrow0 = slice_row0(i + 1);
-                        const uint32_t nstage = (i + 1) % p.stages;
-                        if (nrow0 < p.rows && mbar_try_wait(&full_bar[nstage], ((i + 1) / p.stages) & 1u)) {
-                            const unsigned char *nst = ring + (size_t)nstage * L.stage_bytes;
-                            const uint32_t *nrp = reinterpret_cast<const uint32_t *>(nst + L.rp_off);
-                            pf.s_next = nrp[0];
-                            pf.e_next = nrp[min(p.R, p.rows - (uint32_t)nrow0)];
-                            pf.ci_next = reinterpret_cast<const uint32_t *>(nst + L.idx_off) - (pf.s_next & ~3u);
-                        }
-                    }
-                }
-            }
             if constexpr (STAGED)
                 process_slice<T, V, G, NT, FULLN, U>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                      reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes, c_bytes,
-                                                     col_ok, grp, streaming, pf);
+                                                     col_ok, grp, streaming);
             else
-                process_slice<T, V, G, NT, FULLN, U>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, streaming, pf);
+                process_slice<T, V, G, NT, FULLN, U>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, streaming);
         }
     }
 }

@@ -80,9 +80,7 @@ typedef struct bsm_tuning {
     int32_t reg_flavour;     /* vector kernel: register-budget variant. 0 = heuristic; 1 = CTAs of <= 512
                                 threads, 1 per SM; 2 = same with a gather window twice as deep;
                                 3 = CTAs of <= 256 threads, 3 per SM; 4 = <= 256 threads, 4 per SM  */
-    int32_t prefetch_dist;   /* vector kernel: L2 prefetch of far B rows this many entries ahead of the
-                                gather window (0 = heuristic, -1 = off)                             */
-    int32_t reserved[4];
+    int32_t reserved[5];
 } bsm_tuning;
 
 /* what the last bsm_spmm* call on this thread actually launched */
@@ -97,7 +95,8 @@ typedef struct bsm_launch_info {
     int32_t rows_per_slice, stages, capacity;   /* capacity 0 = col_idx/values not staged */
     int32_t passes;          /* column-tile passes                                                  */
     int32_t merge_items, merge_chunks;
-    int32_t rows_per_warp, reg_flavour, col_tile, prefetch_dist;
+    int32_t rows_per_warp, reg_flavour, col_tile;
+    int32_t reserved[1];
 } bsm_launch_info;
 
 /* ------------------------------------------------------------------------------------------
