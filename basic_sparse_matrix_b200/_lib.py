@@ -114,6 +114,7 @@ def _declare(L):
         sig(f"bsm_dense_download_{sfx}", i32, vp, vp)
         sig(f"bsm_mul_dense_host_{sfx}", i32, u64, u64, u64, vp, vp, vp, u64, u64, u64, vp, i32,
             C.POINTER(u64), PV, PV, PV)
+        sig(f"bsm_mul_dense_host_dense_{sfx}", i32, u64, u64, u64, vp, vp, vp, u64, u64, u64, vp, vp, i32)
         sig(f"bsm_mul_vector_{sfx}", i32, vp, vp, u64, vp, u64)
     sig("bsm_csr_from_device", i32, i32, u64, u64, u64, vp, vp, vp, i32, PV)
     sig("bsm_csr_free", i32, vp)

@@ -651,6 +651,100 @@ static int mul_dense_host(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz,
     return BSM_OK;
 }
 
+// Host-to-host dense product, pipelined over groups of columns: column c of C depends on column c of
+// B only, so while group g is multiplied its successor's columns travel host->device and its
+// predecessor's result columns travel device->host (PCIe is full duplex). Three streams, two sets of
+// staging buffers.
+template <typename T>
+static int mul_dense_host_dense(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, const T *v, const uint64_t *col_index,
+                                const uint64_t *row_index, uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                                const T *const *rhs_col_ptrs, T *const *out_col_ptrs, int algo)
+{
+    if (cols != rhs_rows) return fail(BSM_ERR_INCORRECT_DIMENSIONS, "mul_dense: A.cols != rhs.rows (MatErr::IncorrectDimensions)");
+    if (rhs_cols && (!rhs_col_ptrs || !out_col_ptrs)) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense_host_dense: null column pointers");
+    bsm_csr *a = nullptr;
+    BSM_TRY(csr_upload<T>(dtype, rows, cols, nnz, v, col_index, row_index, row_index_len, &a));
+    if (rows == 0 || rhs_cols == 0) {
+        bsm_csr_free(a);
+        return BSM_OK;
+    }
+    const uint64_t w = std::min<uint64_t>(rhs_cols, 32);   // columns per group
+    const uint64_t ngroups = (rhs_cols + w - 1) / w;
+    cudaStream_t user_stream = g_rt.stream, s_in = nullptr, s_mm = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_in_free[2] = {}, ev_c[2] = {}, ev_out_free[2] = {};
+    T *stage_in[2] = {}, *stage_out[2] = {}, *bg[2] = {}, *cg[2] = {};
+    int st = [&]() -> int {
+        BSM_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        BSM_CUDA(cudaStreamCreateWithFlags(&s_mm, cudaStreamNonBlocking));
+        BSM_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            BSM_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            BSM_CUDA(cudaEventCreateWithFlags(&ev_in_free[i], cudaEventDisableTiming));
+            BSM_CUDA(cudaEventCreateWithFlags(&ev_c[i], cudaEventDisableTiming));
+            BSM_CUDA(cudaEventCreateWithFlags(&ev_out_free[i], cudaEventDisableTiming));
+            BSM_CUDA(cudaMalloc(&stage_in[i], w * rhs_rows * sizeof(T)));
+            BSM_CUDA(cudaMalloc(&bg[i], w * rhs_rows * sizeof(T) + 16));
+            BSM_CUDA(cudaMalloc(&cg[i], w * rows * sizeof(T) + 16));
+            BSM_CUDA(cudaMalloc(&stage_out[i], w * rows * sizeof(T)));
+        }
+        for (uint64_t g = 0; g < ngroups; ++g) {
+            const int i = (int)(g & 1);
+            const uint64_t c0 = g * w, gc = std::min<uint64_t>(w, rhs_cols - c0);
+            // host -> device: the group's columns, back to back (column-major staging)
+            if (g >= 2) BSM_CUDA(cudaStreamWaitEvent(s_in, ev_in_free[i], 0));
+            for (uint64_t c = 0; c < gc; ++c) {
+                if (!rhs_col_ptrs[c0 + c] || !out_col_ptrs[c0 + c]) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense_host_dense: null column");
+                BSM_CUDA(cudaMemcpyAsync(stage_in[i] + c * rhs_rows, rhs_col_ptrs[c0 + c], rhs_rows * sizeof(T), cudaMemcpyHostToDevice, s_in));
+            }
+            BSM_CUDA(cudaEventRecord(ev_in[i], s_in));
+            // multiply: column-major -> row-major, C_g = A * B_g, row-major -> column-major
+            BSM_CUDA(cudaStreamWaitEvent(s_mm, ev_in[i], 0));
+            if (g >= 2) BSM_CUDA(cudaStreamWaitEvent(s_mm, ev_out_free[i], 0));
+            BSM_TRY(launch_transpose_cm2rm(dtype, stage_in[i], bg[i], rhs_rows, gc, gc, s_mm));
+            BSM_CUDA(cudaEventRecord(ev_in_free[i], s_mm));
+            bsm_dense bd, cd;
+            bd.dtype = cd.dtype = dtype;
+            bd.rows = rhs_rows;
+            cd.rows = rows;
+            bd.cols = cd.cols = bd.ld = cd.ld = gc;
+            bd.data = bg[i];
+            cd.data = cg[i];
+            bd.owns = cd.owns = false;
+            g_rt.stream = s_mm;
+            const int rc = bsm_spmm(a, &bd, &cd, algo);
+            g_rt.stream = user_stream;
+            BSM_TRY(rc);
+            BSM_TRY(launch_transpose_rm2cm(dtype, cg[i], stage_out[i], rows, gc, gc, s_mm));
+            BSM_CUDA(cudaEventRecord(ev_c[i], s_mm));
+            // device -> host: the group's result columns
+            BSM_CUDA(cudaStreamWaitEvent(s_out, ev_c[i], 0));
+            for (uint64_t c = 0; c < gc; ++c)
+                BSM_CUDA(cudaMemcpyAsync(out_col_ptrs[c0 + c], stage_out[i] + c * rows, rows * sizeof(T), cudaMemcpyDeviceToHost, s_out));
+            BSM_CUDA(cudaEventRecord(ev_out_free[i], s_out));
+        }
+        BSM_CUDA(cudaStreamSynchronize(s_out));
+        BSM_CUDA(cudaStreamSynchronize(s_mm));
+        return BSM_OK;
+    }();
+    g_rt.stream = user_stream;
+    if (st != BSM_OK) cudaDeviceSynchronize();   // nothing may still be using the buffers freed below
+    for (int i = 0; i < 2; ++i) {
+        if (stage_in[i]) cudaFree(stage_in[i]);
+        if (stage_out[i]) cudaFree(stage_out[i]);
+        if (bg[i]) cudaFree(bg[i]);
+        if (cg[i]) cudaFree(cg[i]);
+        if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+        if (ev_in_free[i]) cudaEventDestroy(ev_in_free[i]);
+        if (ev_c[i]) cudaEventDestroy(ev_c[i]);
+        if (ev_out_free[i]) cudaEventDestroy(ev_out_free[i]);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_mm) cudaStreamDestroy(s_mm);
+    if (s_out) cudaStreamDestroy(s_out);
+    bsm_csr_free(a);
+    return st;
+}
+
 template <typename T>
 static int mul_vector(const bsm_csr *a, int dtype, const T *rhs, uint64_t rhs_len, T *out, uint64_t out_len)
 {
@@ -1023,6 +1117,20 @@ int bsm_mul_dense_host_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const flo
 {
     return mul_dense_host<float>(BSM_F32, rows, cols, nnz, v, col_index, row_index, row_index_len, rhs_rows, rhs_cols,
                                  rhs_col_ptrs, algo, out_nnz, out_v, out_col_index, out_row_index);
+}
+int bsm_mul_dense_host_dense_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v, const uint64_t *col_index,
+                                 const uint64_t *row_index, uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                                 const double *const *rhs_col_ptrs, double *const *out_col_ptrs, int algo)
+{
+    return mul_dense_host_dense<double>(BSM_F64, rows, cols, nnz, v, col_index, row_index, row_index_len, rhs_rows, rhs_cols,
+                                        rhs_col_ptrs, out_col_ptrs, algo);
+}
+int bsm_mul_dense_host_dense_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const float *v, const uint64_t *col_index,
+                                 const uint64_t *row_index, uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                                 const float *const *rhs_col_ptrs, float *const *out_col_ptrs, int algo)
+{
+    return mul_dense_host_dense<float>(BSM_F32, rows, cols, nnz, v, col_index, row_index, row_index_len, rhs_rows, rhs_cols,
+                                       rhs_col_ptrs, out_col_ptrs, algo);
 }
 void bsm_host_free(void *p) { free(p); }
 

@@ -200,6 +200,26 @@ class Csr(GetDims):
             L.bsm_host_free(orow)
         return Csr.from_raw_parts((self.dims.rows, rhs.col_count), rv, rc, rr)
 
+    def mul_dense_into(self, rhs: Dense, out: Dense | None = None, algo: str = "auto") -> Dense:
+        """Same product as ``mul_dense`` with a DENSE result in the reference's column-major layout
+        (no zero-drop): host ``Csr`` and host ``Dense`` in, host ``Dense`` out, through the pipelined
+        C-ABI call ``bsm_mul_dense_host_dense_*`` (H2D, multiply and D2H overlap per column group).
+        This is the end-to-end call ``bench.py`` times; pass pinned column buffers for full overlap."""
+        if self.dims.cols != rhs.get_dims().rows:
+            raise MatError(MatErr.IncorrectDimensions)
+        self._check_multipliable()
+        if rhs.dtype != self.dtype:
+            raise TypeError("Csr and Dense must have the same element type")
+        if out is None:
+            out = Dense.new_default_with_dims(rhs.col_count, self.dims.rows, self.dtype)
+        sfx = _lib.suffix(self.dtype)
+        v, ci, ri = self.raw_parts()
+        cols = [np.ascontiguousarray(c) for c in rhs.data]
+        _lib.check(getattr(_lib.lib(), f"bsm_mul_dense_host_dense_{sfx}")(
+            self.dims.rows, self.dims.cols, len(v), _lib.ptr(v), _lib.ptr(ci), _lib.ptr(ri), len(ri),
+            rhs.row_count, rhs.col_count, _lib.col_ptr_array(cols), _lib.col_ptr_array(out.data), _lib.ALGO_NAMES[algo]))
+        return out
+
     def mul_vector(self, rhs, out) -> None:
         """``Csr::mul_vector(&self, rhs:&[T], out:&mut [T]) -> Result<(),MatErr>``
         (sparse.rs:468-482): dense slice in, dense slice out (no zero-drop), computed by the same

@@ -448,12 +448,10 @@ def main():
         d2h = sum(c.nbytes for c in out_cols)
 
         def e2e_step():
-            a_d = gpu.DeviceCsr.from_host(hA)               # H2D values + usize indices, narrowed on device
-            b_d = gpu.DeviceDense.from_host(hB)             # H2D columns + transpose to row-major
-            c_d = a_d.mul_dense(b_d, tuning=tuning)
-            c_d.to_host(hC)                                 # transpose back + D2H columns (synchronises)
-            for h in (a_d, b_d, c_d):
-                h.close()
+            # ONE reference-facing call: host Csr x host Dense -> host Dense. Inside: H2D of A (usize
+            # indices narrowed on the device), then per group of 32 columns H2D of B columns |
+            # transpose + SpMM + transpose | D2H of C columns, overlapped on three streams.
+            hA.mul_dense_into(hB, hC, algo=args.algo)
 
         e2e_step()                                          # warm-up
         torch.cuda.synchronize()
@@ -473,7 +471,8 @@ def main():
         e2e = {"value": round(2.0 * nnz_total * n / te / 1e9, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(te * 1e3, 2), "steps": max(1, args.e2e_steps),
                "matches_device_path": bool(chk),
-               "path": "bsm_csr_upload + bsm_dense_upload (col-major -> row-major) + bsm_spmm + bsm_dense_download, pinned host buffers"}
+               "path": "Csr.mul_dense_into -> bsm_mul_dense_host_dense_f64: host Csr + host Dense columns in, host Dense columns out, "
+                       "column-group pipeline (H2D | transpose+SpMM+transpose | D2H), pinned host buffers"}
         del out_cols
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's CPU path on a bounded sample ------------------

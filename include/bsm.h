@@ -198,6 +198,18 @@ int bsm_mul_dense_host_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const flo
                            uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
                            const float *const *rhs_col_ptrs, int algo, uint64_t *out_nnz,
                            float **out_v, uint64_t **out_col_index, uint64_t **out_row_index);
+/* Same product with a DENSE result in the reference's column-major layout: host Csr and host Dense
+ * columns in, host Dense columns out (out_col_ptrs[c] has room for `rows` elements). Pipelined over
+ * groups of columns so that host->device copies, the multiplication and device->host copies
+ * overlap; use pinned host buffers for the overlap to materialise. */
+int bsm_mul_dense_host_dense_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v,
+                                 const uint64_t *col_index, const uint64_t *row_index,
+                                 uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                                 const double *const *rhs_col_ptrs, double *const *out_col_ptrs, int algo);
+int bsm_mul_dense_host_dense_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const float *v,
+                                 const uint64_t *col_index, const uint64_t *row_index,
+                                 uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                                 const float *const *rhs_col_ptrs, float *const *out_col_ptrs, int algo);
 void bsm_host_free(void *p);
 
 /* Csr::mul_vector(&self, rhs:&[T], out:&mut [T]) -> Result<(),MatErr>  (sparse.rs:468-482):

@@ -291,3 +291,19 @@ def test_device_generators_match_numpy(gpu, dtype):
         assert a == host_csr(dims, v, ci, ri)
         d = gpu.DeviceDense.generate(123, 17, seed=4, mode=mode, offset=0.5, dtype=dtype).to_rowmajor()
         assert np.array_equal(d, gen.dense_rows(123, 17, 4, mode, 0.5, dtype))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 5, 32, 33, 100])
+def test_pipelined_host_to_host_dense_product(gpu, dtype, n):
+    """bsm_mul_dense_host_dense_*: column-group pipeline (H2D | multiply | D2H) == the oracle, bit for bit."""
+    rng = np.random.default_rng(21)
+    m, k = 777, 501
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=7)
+    b = random_dense(rng, k, n, dtype)
+    a = host_csr((m, k), v, ci, ri)
+    out = a.mul_dense_into(Dense.from_data([b[:, c] for c in range(n)], dtype))
+    assert_bitwise(out.to_rowmajor(), ref_numpy.mul_dense_rowmajor(v, ci, ri, b), f"host pipeline n={n}")
+    with pytest.raises(MatError) as e:
+        a.mul_dense_into(Dense.new_default_with_dims(2, k + 1, dtype))
+    assert e.value.kind == MatErr.IncorrectDimensions
