@@ -394,7 +394,8 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (112 * 1024) / resident);
         p.R = R;
         auto smem_now = [&]() {
-            p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 4;
+            // + slack: the vectorised A-stream reads of the kernel run up to two gather windows past the slice
+            p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 36;
             return row_kernel_smem_bytes(a->dtype, p, nw);
         };
         const uint32_t r_floor = sh.G < 32 ? std::max(rq, 2u * rpp) : rq;
@@ -668,7 +669,10 @@ static int mul_dense_host_dense(int dtype, uint64_t rows, uint64_t cols, uint64_
         bsm_csr_free(a);
         return BSM_OK;
     }
-    const uint64_t w = std::min<uint64_t>(rhs_cols, 32);   // columns per group
+    // columns per group: about 1 GB of B per group (deep enough a pipeline at large sizes), 4..32
+    uint64_t w = 32;
+    while (w > 4 && w * rhs_rows * sizeof(T) > ((uint64_t)1 << 30)) w /= 2;
+    w = std::min<uint64_t>(rhs_cols, w);
     const uint64_t ngroups = (rhs_cols + w - 1) / w;
     cudaStream_t user_stream = g_rt.stream, s_in = nullptr, s_mm = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_in_free[2] = {}, ev_c[2] = {}, ev_out_free[2] = {};

@@ -16,6 +16,7 @@
 // within the stated tolerance of the reference (and exact for exactly representable data).
 #include "bsm_common.cuh"
 #include "kernels.h"
+#include "spmm_stream.cuh"
 
 namespace bsm {
 
@@ -43,20 +44,21 @@ __global__ void merge_partition_kernel(const uint32_t *__restrict__ row_ptr, uin
     part_rows[c] = lo;
 }
 
-template <typename T, int V, int G, int NT>
+constexpr uint32_t kMergeSlack = 40;   // staged arrays are padded: the gather engine's LDS.128 run past the chunk
+
+template <typename T, int V, int G, int NT, bool FULLN, int U>
 __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
 
-    constexpr int U = NT >= 4 ? 2 : (NT == 2 ? 4 : 8);
     const uint32_t groups_per_cta = (blockDim.x / 32) * (32 / G);
     const uint32_t span = groups_per_cta * p.items;   // merge items per CTA
 
-    // shared layout: vals[span+4] | idx[span+4] | rp[span+8]
+    // shared layout: vals[span+slack] | idx[span+slack] | rp[span+8]
     T *val_s = reinterpret_cast<T *>(smem);
-    uint32_t *idx_s = reinterpret_cast<uint32_t *>(smem + (size_t)(span + 4) * sizeof(T));
-    uint32_t *rp_s = idx_s + (span + 4);
+    uint32_t *idx_s = reinterpret_cast<uint32_t *>(smem + (size_t)(span + kMergeSlack) * sizeof(T));
+    uint32_t *rp_s = idx_s + (span + kMergeSlack);
 
     const uint32_t c0 = blockIdx.x * groups_per_cta;
     const uint32_t cend = min(c0 + groups_per_cta, p.num_chunks);
@@ -100,9 +102,10 @@ __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
     }
     bool col_ok[NT];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) col_ok[t] = (uint32_t)((t * G + gl) * V) < p.n;
-    const T *__restrict__ b_lane = static_cast<const T *>(p.B) + gl * V;
-    T *__restrict__ c_lane = static_cast<T *>(p.C) + gl * V;
+    for (int t = 0; t < NT; ++t) col_ok[t] = FULLN || (uint32_t)((t * G + gl) * V) < p.n;
+    const char *__restrict__ b_bytes = reinterpret_cast<const char *>(static_cast<const T *>(p.B) + gl * V);
+    const uint32_t ldb_bytes = p.ldb * (uint32_t)sizeof(T);
+    const uint32_t ldc_bytes = p.ldc * (uint32_t)sizeof(T);
     const bool streaming = (p.flags & BSM_TUNE_C_STREAMING) != 0;
 
     mbar_wait(&bar, 0);   // staged slices have landed
@@ -112,45 +115,28 @@ __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[t].zero();
     bool dirty = false;   // entries accumulated since the last row close
-    uint32_t row_end = row < row_next ? rp_s[row + 1 - rp_a] : kNoCarry;
+    const uint32_t *rp_rel = rp_s - rp_a;   // row_ptr[i] at rp_rel[i]
+    uint32_t row_end = row < row_next ? rp_rel[row + 1] : kNoCarry;
+    char *crow = reinterpret_cast<char *>(static_cast<T *>(p.C) + gl * V) + (size_t)row * ldc_bytes;
 
     auto close_row = [&]() {
-        T *crow = c_lane + (size_t)row * p.ldc;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            if (col_ok[t]) acc[t].store(crow + t * G * V, streaming);
+            if (FULLN || col_ok[t]) acc[t].store(reinterpret_cast<T *>(crow) + t * G * V, streaming);
             acc[t].zero();
         }
+        crow += ldc_bytes;
         dirty = false;
         ++row;
-        row_end = row < row_next ? rp_s[row + 1 - rp_a] : kNoCarry;
+        row_end = row < row_next ? rp_rel[row + 1] : kNoCarry;
     };
 
-    for (uint32_t e0 = nz; e0 < nz_end; e0 += U) {
-        Lane<T, V> b[U][NT];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (e0 + u < nz_end) {
-                const uint32_t col = idx_s[e0 + u - z_a];
-                const T *brow = b_lane + (size_t)col * p.ldb;
-#pragma unroll
-                for (int t = 0; t < NT; ++t)
-                    if (col_ok[t]) b[u][t].load(brow + t * G * V, false);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (e0 + u < nz_end) {
-                while (e0 + u >= row_end) close_row();   // rows (possibly empty) ending before this entry
-                const T a = val_s[e0 + u - z_a];
-#pragma unroll
-                for (int t = 0; t < NT; ++t)
-#pragma unroll
-                    for (int i = 0; i < V; ++i) acc[t].x[i] = mul_add<true>(a, b[u][t].x[i], acc[t].x[i]);
-                dirty = true;
-            }
-        }
-    }
+    // stored order inside the chunk, FMA; rows (possibly empty) that end before an entry are closed first
+    stream_entries<T, V, NT, FULLN, U, true, true>(idx_s - z_a, val_s - z_a, nz, nz_end, b_bytes, ldb_bytes, col_ok, G, acc,
+                                                   [&](uint32_t k) {
+                                                       while (k >= row_end) close_row();
+                                                       dirty = true;
+                                                   });
     while (row < row_next) close_row();   // rows ending exactly at the chunk end, trailing empty rows
 
     // whatever is left belongs to row_next, which a later chunk closes
@@ -159,7 +145,7 @@ __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
         T *car = static_cast<T *>(p.carry_vals) + (size_t)c * p.ldcar + gl * V;
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-            if (col_ok[t]) acc[t].store(car + t * G * V, false);
+            if (FULLN || col_ok[t]) acc[t].store(car + t * G * V, false);
     }
 }
 
@@ -199,39 +185,44 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeParams p)
 // ------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------
-template <typename T, int V, int G, int NT> static const void *merge_kernel_ptr()
+constexpr int merge_default_u(int NT) { return NT >= 4 ? 4 : (NT == 2 ? 4 : 8); }
+
+template <typename T, int V, int G, int NT> static const void *merge_kernel_ptr(bool fulln)
 {
-    return reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT>);
+    constexpr int U = merge_default_u(NT);
+    return fulln ? reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT, true, U>)
+                 : reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT, false, U>);
 }
-template <typename T, int V> static const void *merge_kernel_select_gnt(int G, int NT)
+template <typename T, int V> static const void *merge_kernel_select_gnt(int G, int NT, bool fulln)
 {
     if (G == 32) {
         switch (NT) {
-            case 1: return merge_kernel_ptr<T, V, 32, 1>();
-            case 2: return merge_kernel_ptr<T, V, 32, 2>();
-            case 4: return merge_kernel_ptr<T, V, 32, 4>();
+            case 1: return merge_kernel_ptr<T, V, 32, 1>(fulln);
+            case 2: return merge_kernel_ptr<T, V, 32, 2>(fulln);
+            case 4: return merge_kernel_ptr<T, V, 32, 4>(fulln);
         }
         return nullptr;
     }
     if (NT != 1) return nullptr;
     switch (G) {
-        case 16: return merge_kernel_ptr<T, V, 16, 1>();
-        case 8: return merge_kernel_ptr<T, V, 8, 1>();
-        case 4: return merge_kernel_ptr<T, V, 4, 1>();
-        case 2: return merge_kernel_ptr<T, V, 2, 1>();
-        case 1: return merge_kernel_ptr<T, V, 1, 1>();
+        case 16: return merge_kernel_ptr<T, V, 16, 1>(fulln);
+        case 8: return merge_kernel_ptr<T, V, 8, 1>(fulln);
+        case 4: return merge_kernel_ptr<T, V, 4, 1>(fulln);
+        case 2: return merge_kernel_ptr<T, V, 2, 1>(fulln);
+        case 1: return merge_kernel_ptr<T, V, 1, 1>(fulln);
     }
     return nullptr;
 }
-static const void *merge_kernel_select(int dtype, Shape sh)
+static const void *merge_kernel_select(int dtype, Shape sh, uint32_t n)
 {
+    const bool fulln = n == (uint32_t)(sh.V * sh.G * sh.NT);
     if (dtype == BSM_F64) {
-        if (sh.V == 1) return merge_kernel_select_gnt<double, 1>(sh.G, sh.NT);
-        if (sh.V == 2) return merge_kernel_select_gnt<double, 2>(sh.G, sh.NT);
+        if (sh.V == 1) return merge_kernel_select_gnt<double, 1>(sh.G, sh.NT, fulln);
+        if (sh.V == 2) return merge_kernel_select_gnt<double, 2>(sh.G, sh.NT, fulln);
     } else {
-        if (sh.V == 1) return merge_kernel_select_gnt<float, 1>(sh.G, sh.NT);
-        if (sh.V == 2) return merge_kernel_select_gnt<float, 2>(sh.G, sh.NT);
-        if (sh.V == 4) return merge_kernel_select_gnt<float, 4>(sh.G, sh.NT);
+        if (sh.V == 1) return merge_kernel_select_gnt<float, 1>(sh.G, sh.NT, fulln);
+        if (sh.V == 2) return merge_kernel_select_gnt<float, 2>(sh.G, sh.NT, fulln);
+        if (sh.V == 4) return merge_kernel_select_gnt<float, 4>(sh.G, sh.NT, fulln);
     }
     return nullptr;
 }
@@ -239,7 +230,7 @@ static const void *merge_kernel_select(int dtype, Shape sh)
 size_t merge_kernel_smem_bytes(int dtype, Shape sh, int block, uint32_t items)
 {
     const size_t span = (size_t)(block / 32) * (32 / sh.G) * items;
-    return (span + 4) * dtype_size(dtype) + (span + 4) * 4 + (span + 8) * 4;
+    return (span + kMergeSlack) * dtype_size(dtype) + (span + kMergeSlack) * 4 + (span + 8) * 4;
 }
 
 int launch_merge_partition(const uint32_t *row_ptr, uint32_t rows, uint32_t nnz, uint32_t items, uint32_t num_chunks,
@@ -255,7 +246,7 @@ int launch_merge_partition(const uint32_t *row_ptr, uint32_t rows, uint32_t nnz,
 
 int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, cudaStream_t stream, int *grid_out)
 {
-    const void *k = merge_kernel_select(dtype, sh);
+    const void *k = merge_kernel_select(dtype, sh, p.n);
     if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_merge: no kernel for this lane shape");
     const uint32_t groups_per_cta = (uint32_t)(block / 32) * (32 / sh.G);
     const uint32_t grid = (p.num_chunks + groups_per_cta - 1) / groups_per_cta;

@@ -27,6 +27,7 @@
 #pragma once
 #include "bsm_common.cuh"
 #include "kernels.h"
+#include "spmm_stream.cuh"
 
 namespace bsm {
 
@@ -45,29 +46,11 @@ __host__ __device__ inline RowSmemLayout row_layout(uint32_t cap, uint32_t R, ui
     return l;
 }
 
-// B row `c` of this lane: b_bytes already points at the lane's first column
-template <typename T, int V, int NT, bool FULLN>
-__device__ __forceinline__ void load_brow(Lane<T, V> (&b)[NT], const char *__restrict__ b_bytes, uint32_t ldb_bytes, uint32_t c,
-                                          const bool (&col_ok)[NT], int G)
-{
-    const T *brow = reinterpret_cast<const T *>(b_bytes + (size_t)c * ldb_bytes);   // one IMAD.WIDE
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-        if (FULLN || col_ok[t]) b[t].load(brow + t * G * V, false);
-}
-
-template <typename T, int V, int NT>
-__device__ __forceinline__ void fma_row(Lane<T, V> (&acc)[NT], const Lane<T, V> (&b)[NT], T a)
-{
-#pragma unroll
-    for (int t = 0; t < NT; ++t)
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc[t].x[i] = mul_add<false>(a, b[t].x[i], acc[t].x[i]);   // sparse.rs:438-439
-}
-
 // One slice of one warp: rows [row0, row0+nr), entry k of the matrix at ci[k - base] / va[k - base]
 // (shared memory when the slice was staged by TMA, else the global arrays with base = 0).
-template <typename T, int V, int G, int NT, bool FULLN, int U>
+// VECA: col_idx / values sit in a 16-byte aligned shared-memory stage (padded past the slice), so the A
+// stream is read four columns / two or four values per LDS.128 instead of one scalar LDS per entry.
+template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA>
 __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t *__restrict__ rp, const uint32_t *__restrict__ ci,
                                               const T *__restrict__ va, uint32_t base, uint32_t row0, uint32_t nr,
                                               const char *__restrict__ b_bytes, char *__restrict__ c_bytes, const bool (&col_ok)[NT],
@@ -97,34 +80,9 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             ++rr;
             row_end = rp[min(rr + 1u, nr)];
         };
-        // rolling window of U gathers: slot u holds entry k+u until it is consumed and is then
-        // refilled with entry k+u+U at once, so U gathers stay in flight whatever the row lengths
-        // (the prologue loads every slot unconditionally — past the end it re-reads the last entry —
-        // so that no slot starts life as a predicated, partially defined register)
-        Lane<T, V> b[U][NT];
-        if (s_all < e_all) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[min(s_all + u, e_all - 1u)], col_ok, G);
-        }
-        uint32_t k = s_all;
-        for (; k + 2 * U <= e_all; k += U) {   // steady state: no bounds checks
-#pragma unroll
-            for (int u = 0; u < U; ++u) {      // consumed strictly in stored order
-                while (k + u == row_end) close_row();
-                fma_row<T, V, NT>(acc, b[u], va[k + u]);
-                load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
-            }
-        }
-        for (; k < e_all; k += U) {            // drain
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (k + u < e_all) {
-                    while (k + u == row_end) close_row();
-                    fma_row<T, V, NT>(acc, b[u], va[k + u]);
-                    if (k + u + U < e_all) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
-                }
-            }
-        }
+        stream_entries<T, V, NT, FULLN, U, VECA, false>(ci, va, s_all, e_all, b_bytes, ldb_bytes, col_ok, G, acc, [&](uint32_t k) {
+            while (k == row_end) close_row();
+        });
         while (rr < nr) close_row();   // the last row with entries, then trailing empty rows
     } else {
         // ======== 32/G rows side by side, row by row ========
@@ -133,28 +91,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             Lane<T, V> acc[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) acc[t].zero();
-            Lane<T, V> b[U][NT];
-            if (s < e) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[min(s + u, e - 1u)], col_ok, G);
-            }
-            uint32_t k = s;
-            for (; k + 2 * U <= e; k += U) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    fma_row<T, V, NT>(acc, b[u], va[k + u]);
-                    load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
-                }
-            }
-            for (; k < e; k += U) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (k + u < e) {
-                        fma_row<T, V, NT>(acc, b[u], va[k + u]);
-                        if (k + u + U < e) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[k + u + U], col_ok, G);
-                    }
-                }
-            }
+            stream_entries<T, V, NT, FULLN, U, false, false>(ci, va, s, e, b_bytes, ldb_bytes, col_ok, G, acc, [](uint32_t) {});
             T *crow = reinterpret_cast<T *>(c_bytes + (size_t)(row0 + r) * ldc_bytes);
 #pragma unroll
             for (int t = 0; t < NT; ++t)
@@ -260,11 +197,11 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
             const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
             const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
             if constexpr (STAGED)
-                process_slice<T, V, G, NT, FULLN, U>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
+                process_slice<T, V, G, NT, FULLN, U, true>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                      reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes, c_bytes,
                                                      col_ok, grp, streaming);
             else
-                process_slice<T, V, G, NT, FULLN, U>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, streaming);
+                process_slice<T, V, G, NT, FULLN, U, false>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, streaming);
         }
     }
 }
