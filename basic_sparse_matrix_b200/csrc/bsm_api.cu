@@ -112,15 +112,19 @@ static int detect_row_stride(bsm_csr *a)
 static int compute_stats(bsm_csr *a)
 {
     uint32_t *d = nullptr;
-    BSM_CUDA(cudaMallocAsync(&d, 8, g_rt.stream));
-    BSM_CUDA(cudaMemsetAsync(d, 0, 8, g_rt.stream));
+    BSM_CUDA(cudaMallocAsync(&d, 16, g_rt.stream));
+    const uint32_t init[4] = {0u, 0u, 0xFFFFFFFFu, 0u};   // max row length, bad flag, min column, max column
+    BSM_CUDA(cudaMemcpyAsync(d, init, 16, cudaMemcpyHostToDevice, g_rt.stream));
     BSM_TRY(launch_row_stats(a->row_ptr, a->rows, d, d + 1, g_rt.stream));
-    uint32_t h[2] = {0, 0};
-    BSM_CUDA(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, g_rt.stream));
+    BSM_TRY(launch_col_range(a->col_idx, a->nnz, d + 2, g_rt.stream));
+    uint32_t h[4] = {0, 0, 0, 0};
+    BSM_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, g_rt.stream));
     BSM_CUDA(cudaFreeAsync(d, g_rt.stream));
     BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
     if (h[1]) return fail(BSM_ERR_INVALID_ARGUMENT, "row_index is not non-decreasing");
     a->max_row_nnz = h[0];
+    a->col_min = a->nnz ? h[2] : 0;
+    a->col_max = a->nnz ? h[3] : 0;
     return detect_row_stride(a);
 }
 
@@ -391,11 +395,12 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // global memory instead (unstaged variant).
         const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
         const int resident = flavour == 2 ? 3 : (flavour == 3 ? 4 : 1);
-        const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (112 * 1024) / resident);
+        const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (128 * 1024) / resident);
+        const uint32_t window = (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight (U)
         p.R = R;
         auto smem_now = [&]() {
             // + slack: the vectorised A-stream reads of the kernel run up to two gather windows past the slice
-            p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 36;
+            p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 2 * window + 4;
             return row_kernel_smem_bytes(a->dtype, p, nw);
         };
         const uint32_t r_floor = sh.G < 32 ? std::max(rq, 2u * rpp) : rq;
@@ -493,7 +498,7 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
         const uint32_t num_chunks = (uint32_t)((total + items - 1) / items);
         if (num_chunks == 0) continue;
         BSM_TRY(ensure_partition(a, items, num_chunks));
-        const size_t need_vals = (size_t)num_chunks * ldcar * s, need_rows = (size_t)num_chunks * 4;
+        const size_t need_vals = (size_t)num_chunks * ldcar * s;
         if (a->carry_vals_bytes < need_vals) {
             if (a->carry_vals) cudaFree(a->carry_vals);
             a->carry_vals = nullptr;
@@ -501,12 +506,14 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
             BSM_CUDA(cudaMalloc(&a->carry_vals, need_vals));
             a->carry_vals_bytes = need_vals;
         }
-        if (a->carry_rows_bytes < need_rows) {
-            if (a->carry_rows) cudaFree(a->carry_rows);
-            a->carry_rows = nullptr;
-            a->carry_rows_bytes = 0;
-            BSM_CUDA(cudaMalloc(&a->carry_rows, need_rows));
-            a->carry_rows_bytes = need_rows;
+        // rows whose run of carries exceeds 64 chunks need more than 64*items entries: at most this many
+        const uint64_t long_cap = a->nnz / (64ull * items) + 1;
+        if (a->long_rows_cap < long_cap) {
+            if (a->long_rows) cudaFree(a->long_rows);
+            a->long_rows = nullptr;
+            a->long_rows_cap = 0;
+            BSM_CUDA(cudaMalloc(&a->long_rows, (2 * long_cap + 1) * 4));
+            a->long_rows_cap = long_cap;
         }
         MergeParams p{};
         p.row_ptr = a->row_ptr;
@@ -516,7 +523,9 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
         p.C = (char *)c->data + (size_t)col0 * s;
         p.part_rows = a->part_rows;
         p.carry_vals = a->carry_vals;
-        p.carry_rows = a->carry_rows;
+        p.long_rows = a->long_rows;
+        p.long_count = a->long_rows + 2 * a->long_rows_cap;
+        p.long_cap = (uint32_t)a->long_rows_cap;
         p.rows = (uint32_t)a->rows;
         p.nnz = (uint32_t)a->nnz;
         p.n = n;
@@ -530,8 +539,9 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
         if (smem > (size_t)g_rt.max_smem_optin - 1024) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_merge: items do not fit shared memory");
         int grid = 0;
         BSM_TRY(launch_spmm_merge(a->dtype, sh, p, block, smem, g_rt.stream, &grid));
-        BSM_TRY(launch_merge_fixup(a->dtype, p, g_rt.stream));
-        g_info.kernels += 2;
+        int fix_launches = 0;
+        BSM_TRY(launch_merge_fixup(a->dtype, p, g_rt.stream, &fix_launches));
+        g_info.kernels += 1 + fix_launches;
         g_info.vec_elems = sh.V;
         g_info.lanes_per_row = sh.G;
         g_info.reg_tiles = sh.NT;
@@ -674,6 +684,7 @@ static int mul_dense_host_dense(int dtype, uint64_t rows, uint64_t cols, uint64_
     while (w > 4 && w * rhs_rows * sizeof(T) > ((uint64_t)1 << 30)) w /= 2;
     w = std::min<uint64_t>(rhs_cols, w);
     const uint64_t ngroups = (rhs_cols + w - 1) / w;
+    const uint64_t win_lo = a->nnz ? a->col_min : 0, win_rows = a->nnz ? (uint64_t)a->col_max - a->col_min + 1 : 0;
     cudaStream_t user_stream = g_rt.stream, s_in = nullptr, s_mm = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_in_free[2] = {}, ev_c[2] = {}, ev_out_free[2] = {};
     T *stage_in[2] = {}, *stage_out[2] = {}, *bg[2] = {}, *cg[2] = {};
@@ -698,7 +709,11 @@ static int mul_dense_host_dense(int dtype, uint64_t rows, uint64_t cols, uint64_
             if (g >= 2) BSM_CUDA(cudaStreamWaitEvent(s_in, ev_in_free[i], 0));
             for (uint64_t c = 0; c < gc; ++c) {
                 if (!rhs_col_ptrs[c0 + c] || !out_col_ptrs[c0 + c]) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense_host_dense: null column");
-                BSM_CUDA(cudaMemcpyAsync(stage_in[i] + c * rhs_rows, rhs_col_ptrs[c0 + c], rhs_rows * sizeof(T), cudaMemcpyHostToDevice, s_in));
+                // only the rows of B that A references travel (a rank's row block of a banded / stencil
+                // matrix reads a window of B, not all of it); the rest of the staging is never gathered
+                if (win_rows)
+                    BSM_CUDA(cudaMemcpyAsync(stage_in[i] + c * rhs_rows + win_lo, rhs_col_ptrs[c0 + c] + win_lo, win_rows * sizeof(T),
+                                             cudaMemcpyHostToDevice, s_in));
             }
             BSM_CUDA(cudaEventRecord(ev_in[i], s_in));
             // multiply: column-major -> row-major, C_g = A * B_g, row-major -> column-major
@@ -970,7 +985,7 @@ int bsm_csr_free(bsm_csr *a)
     }
     if (a->part_rows) cudaFree(a->part_rows);
     if (a->carry_vals) cudaFree(a->carry_vals);
-    if (a->carry_rows) cudaFree(a->carry_rows);
+    if (a->long_rows) cudaFree(a->long_rows);
     delete a;
     return BSM_OK;
 }

@@ -60,6 +60,7 @@ struct bsm_csr {
     uint32_t *row_ptr = nullptr;   // u32[rows+1]
     bool owns = true;
     uint64_t max_row_nnz = 0;      // csr_row_stats (dispatch heuristic)
+    uint32_t col_min = 0, col_max = 0;   // smallest / largest stored column (valid when nnz > 0)
     uint32_t row_stride = 0;       // dominant off-diagonal column stride of a stencil-like matrix (0 = none)
     // merge-path partition cache (depends only on A and the item count)
     int part_items = 0;
@@ -67,8 +68,8 @@ struct bsm_csr {
     uint32_t *part_rows = nullptr;   // u32[part_chunks+1]: first row each chunk closes
     // carry-out scratch of the merge kernel, grown on demand
     void *carry_vals = nullptr;
-    uint32_t *carry_rows = nullptr;
-    size_t carry_vals_bytes = 0, carry_rows_bytes = 0;
+    uint32_t *long_rows = nullptr;   // [long_cap][2] + counter at the end (merge fix-up of hub rows)
+    size_t carry_vals_bytes = 0, long_rows_cap = 0;
 };
 
 // Device-resident dense matrix, ROW-major with leading dimension ld (elements).

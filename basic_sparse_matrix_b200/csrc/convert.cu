@@ -98,6 +98,35 @@ int launch_row_stats(const uint32_t *row_ptr, uint64_t rows, uint32_t *max_len, 
     return BSM_OK;
 }
 
+// smallest / largest stored column index (which rows of B a matrix — or one rank's row block — reads)
+__global__ void col_range_kernel(const uint32_t *__restrict__ col_idx, uint64_t nnz, uint32_t *min_max)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const uint32_t c = col_idx[i];
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(min_max, lo);
+        atomicMax(min_max + 1, hi);
+    }
+}
+
+int launch_col_range(const uint32_t *col_idx, uint64_t nnz, uint32_t *min_max, cudaStream_t stream)
+{
+    if (nnz == 0) return BSM_OK;
+    col_range_kernel<<<grid_for(nnz, 256), 256, 0, stream>>>(col_idx, nnz, min_max);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
 // ---- layout transposes ---------------------------------------------------------------------------
 // colmajor[c*rows + r]  <->  rowmajor[r*ld + c]; 32x32 tiles through padded shared memory so both
 // sides are coalesced.

@@ -44,11 +44,13 @@ struct MergeParams {
     void *C;
     const uint32_t *part_rows;  // [num_chunks+1]
     void *carry_vals;           // [num_chunks][ldcar]
-    uint32_t *carry_rows;       // [num_chunks]
+    uint32_t *long_rows;        // [long_cap][2]: (row, first carrying chunk) of runs too long for one warp
+    uint32_t *long_count;       // [1]
     uint32_t rows, nnz;
     uint32_t n, ldb, ldc, ldcar;
     uint32_t items;             // merge items (rows + nnz) per lane group
     uint32_t num_chunks;
+    uint32_t long_cap;
     uint32_t flags;
 };
 size_t merge_kernel_smem_bytes(int dtype, Shape sh, int block, uint32_t items);
@@ -56,12 +58,13 @@ int launch_merge_partition(const uint32_t *row_ptr, uint32_t rows, uint32_t nnz,
                            uint32_t num_chunks, uint32_t *part_rows, cudaStream_t stream);
 int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, cudaStream_t stream,
                       int *grid_out);
-int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream);
+int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream, int *launched);
 
 // ---- format conversion / construction (convert.cu) ---------------------------------------------
 int launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t count, uint64_t bound, uint64_t subtract,
                       uint32_t *flag /* set to 1 when (v - subtract) >= bound */, cudaStream_t stream);
 int launch_row_stats(const uint32_t *row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag, cudaStream_t stream);
+int launch_col_range(const uint32_t *col_idx, uint64_t nnz, uint32_t *min_max /* [2], preset to {~0u, 0} */, cudaStream_t stream);
 int launch_transpose_cm2rm(int dtype, const void *colmajor, void *rowmajor, uint64_t rows, uint64_t cols, uint64_t ld,
                            cudaStream_t stream);
 int launch_transpose_rm2cm(int dtype, const void *rowmajor, void *colmajor, uint64_t rows, uint64_t cols, uint64_t ld,

@@ -14,6 +14,8 @@
 //     no atomics): C[row] = (carry_0 + carry_1 + ...) + tail.
 // Long rows are therefore summed as a few partial sums instead of one left-to-right chain —
 // within the stated tolerance of the reference (and exact for exactly representable data).
+#include <algorithm>
+
 #include "bsm_common.cuh"
 #include "kernels.h"
 #include "spmm_stream.cuh"
@@ -140,7 +142,6 @@ __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
     while (row < row_next) close_row();   // rows ending exactly at the chunk end, trailing empty rows
 
     // whatever is left belongs to row_next, which a later chunk closes
-    if (gl == 0) p.carry_rows[c] = dirty ? row_next : kNoCarry;
     if (dirty) {
         T *car = static_cast<T *>(p.carry_vals) + (size_t)c * p.ldcar + gl * V;
 #pragma unroll
@@ -149,28 +150,34 @@ __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
     }
 }
 
-// One warp per chunk; only the first chunk of each run of carry-outs into the same row works.
+// ---- fix-up: C[row] = (carry_first + ... + carry_last) + tail ---------------------------------------
+// Which chunks carry into a row follows from row_ptr alone: entry e of row r is merge item e + r and
+// the row's end is item row_ptr[r+1] + r, so chunks [ (row_ptr[r]+r)/items , (row_ptr[r+1]+r)/items )
+// hold entries of r without closing it (each of them left one carry-out), and the chunk that closes it
+// wrote the tail. Carries are added in chunk order, before the tail (they precede it in stored order).
+constexpr uint32_t kFixupSerialMax = 64;   // longer runs go to the cooperative kernel
+
+// One warp per row. Short runs are summed here; long runs (hub rows of a power-law matrix, thousands of
+// chunks) are queued for merge_fixup_long_kernel.
 template <typename T>
 __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeParams p)
 {
-    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    if (c >= p.num_chunks) return;
-    const uint32_t row = p.carry_rows[c];
-    if (row == kNoCarry) return;
-    if (c > 0 && p.carry_rows[c - 1] == row) return;
-    // run length: chunks c, c+1, ... carrying into the same row (contiguous by construction)
-    uint32_t len = 1;
-    for (;;) {
-        const uint32_t k = c + len + lane;
-        const bool same = k < p.num_chunks && p.carry_rows[k] == row;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, same);
-        if (m == 0xFFFFFFFFu) {
-            len += 32;
-            continue;
+    if (row >= p.rows) return;
+    const uint32_t c = (__ldg(p.row_ptr + row) + row) / p.items;
+    const uint32_t c_close = (__ldg(p.row_ptr + row + 1) + row) / p.items;
+    if (c_close <= c) return;
+    const uint32_t len = c_close - c;
+    if (len > kFixupSerialMax) {
+        if (lane == 0) {
+            const uint32_t slot = atomicAdd(p.long_count, 1u);
+            if (slot < p.long_cap) {
+                p.long_rows[2 * slot] = row;
+                p.long_rows[2 * slot + 1] = c;
+            }
         }
-        len += __ffs(~m) - 1;
-        break;
+        return;
     }
     const T *car = static_cast<const T *>(p.carry_vals);
     T *crow = static_cast<T *>(p.C) + (size_t)row * p.ldc;
@@ -178,7 +185,40 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeParams p)
         T sum = car[(size_t)c * p.ldcar + j];
 #pragma unroll 8
         for (uint32_t k = 1; k < len; ++k) sum += car[(size_t)(c + k) * p.ldcar + j];
-        crow[j] = sum + crow[j];   // carries first (they precede the tail in stored order)
+        crow[j] = sum + crow[j];
+    }
+}
+
+// One CTA (8 warps) per long run: warp w sums the w-th of 8 contiguous segments of the run in chunk
+// order, then the 8 partial sums are combined in segment order — deterministic for a given matrix.
+template <typename T>
+__global__ void __launch_bounds__(256) merge_fixup_long_kernel(const MergeParams p)
+{
+    constexpr uint32_t kMaxN = 4096 / sizeof(T);   // columns of one pass (<= 32 lanes x 16 bytes x 4 tiles)
+    __shared__ T partial[8][kMaxN];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t count = min(*p.long_count, p.long_cap);
+    const T *car = static_cast<const T *>(p.carry_vals);
+    for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const uint32_t row = p.long_rows[2 * i], c = p.long_rows[2 * i + 1];
+        const uint32_t len = (__ldg(p.row_ptr + row + 1) + row) / p.items - c;
+        const uint32_t seg = (len + 7) / 8;
+        const uint32_t k0 = min(warp * seg, len), k1 = min(k0 + seg, len);
+        for (uint32_t j = lane; j < p.n; j += 32) {
+            T sum = T(0);
+#pragma unroll 8
+            for (uint32_t k = k0; k < k1; ++k) sum += car[(size_t)(c + k) * p.ldcar + j];
+            partial[warp][j] = sum;
+        }
+        __syncthreads();
+        T *crow = static_cast<T *>(p.C) + (size_t)row * p.ldc;
+        for (uint32_t j = threadIdx.x; j < p.n; j += blockDim.x) {
+            T sum = partial[0][j];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) sum += partial[w][j];
+            crow[j] = sum + crow[j];
+        }
+        __syncthreads();
     }
 }
 
@@ -260,18 +300,31 @@ int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size
     return BSM_OK;
 }
 
-int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream)
+int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream, int *launched)
 {
-    if (p.num_chunks == 0) return BSM_OK;
+    if (launched) *launched = 0;
+    if (p.num_chunks == 0 || p.rows == 0) return BSM_OK;
     const uint32_t threads = 256;
-    const uint64_t total_threads = (uint64_t)p.num_chunks * 32;
+    const uint64_t total_threads = (uint64_t)p.rows * 32;
     const uint32_t blocks = (uint32_t)((total_threads + threads - 1) / threads);
+    BSM_CUDA(cudaMemsetAsync(p.long_count, 0, 4, stream));
     if (dtype == BSM_F64)
         merge_fixup_kernel<double><<<blocks, threads, 0, stream>>>(p);
     else
         merge_fixup_kernel<float><<<blocks, threads, 0, stream>>>(p);
     BSM_CUDA(cudaGetLastError());
     count_launch();
+    if (launched) ++*launched;
+    if (p.long_cap) {   // a matrix can only have runs longer than kFixupSerialMax chunks if it is that large
+        const uint32_t grid = std::min<uint32_t>(p.long_cap, 592);
+        if (dtype == BSM_F64)
+            merge_fixup_long_kernel<double><<<grid, threads, 0, stream>>>(p);
+        else
+            merge_fixup_long_kernel<float><<<grid, threads, 0, stream>>>(p);
+        BSM_CUDA(cudaGetLastError());
+        count_launch();
+        if (launched) ++*launched;
+    }
     return BSM_OK;
 }
 

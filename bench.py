@@ -444,7 +444,8 @@ def main():
         out_cols = [torch.empty(ai["rows"], dtype=torch.float64 if dt == "f64" else torch.float32).pin_memory().numpy()
                     for _ in range(n)]
         hB, hC = Dense.from_columns_nocopy(host_cols), Dense.from_columns_nocopy(out_cols)
-        h2d = hv.nbytes + hci.nbytes + hri.nbytes + sum(c.nbytes for c in host_cols)
+        # the call uploads only the window of B rows this rank's A block references (all of B at N=1)
+        h2d = hv.nbytes + hci.nbytes + hri.nbytes + k_ref_of(kind, prm, rows_total, r0, r1) * n * s
         d2h = sum(c.nbytes for c in out_cols)
 
         def e2e_step():

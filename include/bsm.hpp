@@ -108,6 +108,8 @@ template <> struct Abi<double> {
     static int dense_upload(uint64_t r, uint64_t c, const double *const *p, bsm_dense **o) { return bsm_dense_upload_f64(r, c, p, o); }
     static int dense_download(const bsm_dense *d, double *const *p) { return bsm_dense_download_f64(d, p); }
     static int mul_vector(const bsm_csr *a, const double *x, uint64_t n, double *y, uint64_t m) { return bsm_mul_vector_f64(a, x, n, y, m); }
+    static int host_dense(uint64_t r, uint64_t c, uint64_t n, const double *v, const uint64_t *ci, const uint64_t *ri, uint64_t l, uint64_t br, uint64_t bc,
+                          const double *const *b, double *const *o) { return bsm_mul_dense_host_dense_f64(r, c, n, v, ci, ri, l, br, bc, b, o, BSM_ALGO_AUTO); }
 };
 template <> struct Abi<float> {
     static constexpr int dtype = BSM_F32;
@@ -116,6 +118,8 @@ template <> struct Abi<float> {
     static int dense_upload(uint64_t r, uint64_t c, const float *const *p, bsm_dense **o) { return bsm_dense_upload_f32(r, c, p, o); }
     static int dense_download(const bsm_dense *d, float *const *p) { return bsm_dense_download_f32(d, p); }
     static int mul_vector(const bsm_csr *a, const float *x, uint64_t n, float *y, uint64_t m) { return bsm_mul_vector_f32(a, x, n, y, m); }
+    static int host_dense(uint64_t r, uint64_t c, uint64_t n, const float *v, const uint64_t *ci, const uint64_t *ri, uint64_t l, uint64_t br, uint64_t bc,
+                          const float *const *b, float *const *o) { return bsm_mul_dense_host_dense_f32(r, c, n, v, ci, ri, l, br, bc, b, o, BSM_ALGO_AUTO); }
 };
 // status -> MatErr where the reference has a matching variant, else throw
 inline bool status_to_materr(int st, MatErr *e)
@@ -271,6 +275,9 @@ template <typename T> class Csr {   // sparse.rs:68-78
 
     // ---- the hot path: Csr::mul_dense(&self, rhs:&Dense<T>) -> Result<Csr<T>,MatErr>  sparse.rs:426-446 ----
     Result<Csr> mul_dense(const Dense<T> &rhs) const;
+    // same product with a DENSE result in the reference's column-major layout (no zero-drop): one pipelined
+    // host-to-host call (H2D | multiply | D2H overlapped per column group)
+    Result<Dense<T>> mul_dense_into_dense(const Dense<T> &rhs) const;
     // Csr::mul_vector(&self, rhs:&[T], out:&mut [T]) -> Result<(),MatErr>  sparse.rs:468-482
     Result<void> mul_vector(const std::vector<T> &rhs, std::vector<T> &out) const;
 };
@@ -427,6 +434,26 @@ template <typename T> Result<Csr<T>> Csr<T>::mul_dense(const Dense<T> &rhs) cons
     auto c = da.mul_dense(db);
     if (c.is_err()) return Result<Csr<T>>(c.unwrap_err());
     return Result<Csr<T>>(c.unwrap().into_csr().to_host());
+}
+
+template <typename T> Result<Dense<T>> Csr<T>::mul_dense_into_dense(const Dense<T> &rhs) const
+{
+    const MatDim bd = rhs.get_dims();
+    if (dims_.cols != bd.rows) return Result<Dense<T>>(MatErr::IncorrectDimensions);   // sparse.rs:427-429
+    Dense<T> out = Dense<T>::new_default_with_dims(bd.cols, dims_.rows);
+    std::vector<const T *> in_ptrs;
+    std::vector<T *> out_ptrs;
+    for (const auto &c : rhs.columns()) in_ptrs.push_back(c.data());
+    for (auto &c : out.columns_mut()) out_ptrs.push_back(c.data());
+    const int st = detail::Abi<T>::host_dense(dims_.rows, dims_.cols, v_.size(), v_.data(), reinterpret_cast<const uint64_t *>(col_index_.data()),
+                                              reinterpret_cast<const uint64_t *>(row_index_.data()), row_index_.size(), bd.rows, bd.cols,
+                                              in_ptrs.data(), out_ptrs.data());
+    MatErr e;
+    if (st != BSM_OK) {
+        if (detail::status_to_materr(st, &e)) return Result<Dense<T>>(e);
+        detail::throw_status(st);
+    }
+    return Result<Dense<T>>(std::move(out));
 }
 
 template <typename T> Result<void> Csr<T>::mul_vector(const std::vector<T> &rhs, std::vector<T> &out) const

@@ -55,6 +55,13 @@ extern "C" {
     /// Result construction of mul_dense: insert's zero-drop + finalise (sparse.rs:442, 222-233, 206-219).
     pub fn bsm_dense_to_csr(d: *const bsm_dense, out: *mut *mut bsm_csr) -> c_int;
 
+    /// host Csr x host Dense -> host Dense (column-major), pipelined H2D | multiply | D2H per column group
+    pub fn bsm_mul_dense_host_dense_f64(rows: u64, cols: u64, nnz: u64, v: *const f64, col_index: *const u64, row_index: *const u64,
+                                        row_index_len: u64, rhs_rows: u64, rhs_cols: u64, rhs_col_ptrs: *const *const f64,
+                                        out_col_ptrs: *const *mut f64, algo: c_int) -> c_int;
+    pub fn bsm_mul_dense_host_dense_f32(rows: u64, cols: u64, nnz: u64, v: *const f32, col_index: *const u64, row_index: *const u64,
+                                        row_index_len: u64, rhs_rows: u64, rhs_cols: u64, rhs_col_ptrs: *const *const f32,
+                                        out_col_ptrs: *const *mut f32, algo: c_int) -> c_int;
     pub fn bsm_mul_vector_f64(a: *const bsm_csr, rhs: *const f64, rhs_len: u64, out: *mut f64, out_len: u64) -> c_int;
     pub fn bsm_mul_vector_f32(a: *const bsm_csr, rhs: *const f32, rhs_len: u64, out: *mut f32, out_len: u64) -> c_int;
 

@@ -78,6 +78,8 @@ template <typename T> static void multiplication_tests()
         Csr<T> output_ref = Csr<T>::from_data({{9, 29, 49}, {7, 35, 63}, {8, 20, 32}, {3, 7, 11}, {1, 5, 9}});
         Csr<T> output = m.mul_dense(a).unwrap();
         CHECK(output_ref == output);
+        // the same product through the pipelined host-to-host call, dense (column-major) result
+        CHECK(m.mul_dense_into_dense(a).unwrap() == Dense<T>::from_data({{9, 7, 8, 3, 1}, {29, 35, 20, 7, 5}, {49, 63, 32, 11, 9}}));
     }
     {   // test_nnz (sparse.rs:1153-1178): zero outputs are dropped by insert
         Dense<T> a = Dense<T>::from_data({{1, 0, 3, 4}, {8, 0, 0, 5}});
