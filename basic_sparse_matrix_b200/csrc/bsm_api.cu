@@ -2,6 +2,7 @@
 // with format conversion, kernel dispatch heuristics, sharding helpers, generators.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -383,7 +384,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         R = std::max(rq, R / rq * rq);
         // register-budget flavour (spmm_rows_inst.cuh); flavours 2 and 3 exist for full-width G == 32 shapes
         const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
-        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 4) - 1 : (wide_full && !user_nw ? 2 : 0);
+        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 5) - 1 : (wide_full && !user_nw ? 2 : 0);
         if (!wide_full) flavour = 0;
         if (flavour >= 2 && nw > 8) nw = 8;
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
@@ -394,7 +395,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // hardware limit. If even the smallest slice cannot be staged, col_idx / values are read from
         // global memory instead (unstaged variant).
         const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
-        const int resident = flavour == 2 ? 3 : (flavour == 3 ? 4 : 1);
+        const int resident = (flavour == 2 || flavour == 4) ? 3 : (flavour == 3 ? 4 : 1);
         const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (128 * 1024) / resident);
         const uint32_t window = (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight (U)
         p.R = R;
@@ -492,7 +493,7 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
         const int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 8) : 8;
         const int block = nw * 32;
         const uint32_t groups = (uint32_t)nw * (32u / sh.G);
-        uint32_t items = tn.merge_items > 0 ? (uint32_t)tn.merge_items : (sh.G == 32 ? 256u : std::max(16u, 2048u / groups));
+        uint32_t items = tn.merge_items > 0 ? (uint32_t)tn.merge_items : (sh.G == 32 ? 384u : std::max(16u, 2048u / groups));
         items = (uint32_t)round_up(items, 4);
         if (total + items >= 0xFFFFFFF0ull) return fail(BSM_ERR_INDEX_OVERFLOW, "spmm_merge: rows+nnz must fit u32");
         const uint32_t num_chunks = (uint32_t)((total + items - 1) / items);
@@ -1118,6 +1119,29 @@ int bsm_last_launch_info(bsm_launch_info *info)
     return BSM_OK;
 }
 uint64_t bsm_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int bsm_dense_residual_norm(const bsm_dense *ax, const bsm_dense *b, double *resid_fro, double *b_fro)
+{
+    BSM_TRY(ensure_init());
+    if (!ax || !b || !resid_fro || !b_fro) return fail(BSM_ERR_INVALID_ARGUMENT, "residual_norm: null argument");
+    if (ax->rows != b->rows || ax->cols != b->cols) return fail(BSM_ERR_INCORRECT_DIMENSIONS, "residual_norm: shapes differ");
+    if (ax->dtype != b->dtype) return fail(BSM_ERR_DTYPE_MISMATCH, "residual_norm: dtype mismatch");
+    const int nd = residual_norm_scratch_doubles();
+    double *d = nullptr;
+    BSM_CUDA(cudaMalloc(&d, nd * sizeof(double)));
+    int st = launch_residual_norms(ax->dtype, ax->data, ax->ld, b->data, b->ld, ax->rows, ax->cols, d, g_rt.stream);
+    double h[2] = {0.0, 0.0};
+    if (st == BSM_OK) {
+        cudaError_t e = cudaMemcpyAsync(h, d + nd - 2, 16, cudaMemcpyDeviceToHost, g_rt.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_rt.stream);
+        if (e != cudaSuccess) st = fail(BSM_ERR_CUDA, std::string("residual_norm: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    if (st != BSM_OK) return st;
+    *resid_fro = std::sqrt(h[0]);
+    *b_fro = std::sqrt(h[1]);
+    return BSM_OK;
+}
 
 int bsm_dense_to_csr(const bsm_dense *d, bsm_csr **out) { return dense_to_csr_impl(d, out); }
 

@@ -127,6 +127,70 @@ int launch_col_range(const uint32_t *col_idx, uint64_t nnz, uint32_t *min_max, c
     return BSM_OK;
 }
 
+// ---- residual norms: ||X - Y||_F^2 and ||Y||_F^2 (f64 accumulation, fixed grid -> deterministic) ----
+constexpr int kNormBlocks = 1184, kNormThreads = 256;
+
+template <typename T>
+__global__ void residual_partial_kernel(const T *__restrict__ x, uint64_t ldx, const T *__restrict__ y, uint64_t ldy, uint64_t rows,
+                                        uint64_t cols, double *__restrict__ partial)
+{
+    __shared__ double sh[2][kNormThreads / 32];
+    double d2 = 0.0, y2 = 0.0;
+    const uint64_t total = rows * cols;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / cols, c = i - r * cols;
+        const double xv = (double)x[r * ldx + c], yv = (double)y[r * ldy + c];
+        d2 += (xv - yv) * (xv - yv);
+        y2 += yv * yv;
+    }
+    for (int o = 16; o; o >>= 1) {
+        d2 += __shfl_xor_sync(0xFFFFFFFFu, d2, o);
+        y2 += __shfl_xor_sync(0xFFFFFFFFu, y2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = d2;
+        sh[1][threadIdx.x >> 5] = y2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kNormThreads / 32; ++w) {
+            a += sh[0][w];
+            b += sh[1][w];
+        }
+        partial[2 * blockIdx.x] = a;
+        partial[2 * blockIdx.x + 1] = b;
+    }
+}
+
+__global__ void residual_final_kernel(const double *__restrict__ partial, int blocks, double *__restrict__ out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < blocks; ++i) {
+            a += partial[2 * i];
+            b += partial[2 * i + 1];
+        }
+        out[0] = a;
+        out[1] = b;
+    }
+}
+
+int launch_residual_norms(int dtype, const void *x, uint64_t ldx, const void *y, uint64_t ldy, uint64_t rows, uint64_t cols,
+                          double *partial /* [2*kNormBlocks + 2] */, cudaStream_t stream)
+{
+    if (dtype == BSM_F64)
+        residual_partial_kernel<double><<<kNormBlocks, kNormThreads, 0, stream>>>((const double *)x, ldx, (const double *)y, ldy, rows, cols, partial);
+    else
+        residual_partial_kernel<float><<<kNormBlocks, kNormThreads, 0, stream>>>((const float *)x, ldx, (const float *)y, ldy, rows, cols, partial);
+    BSM_CUDA(cudaGetLastError());
+    residual_final_kernel<<<1, 32, 0, stream>>>(partial, kNormBlocks, partial + 2 * kNormBlocks);
+    BSM_CUDA(cudaGetLastError());
+    count_launch(2);
+    return BSM_OK;
+}
+int residual_norm_scratch_doubles() { return 2 * kNormBlocks + 2; }
+
 // ---- layout transposes ---------------------------------------------------------------------------
 // colmajor[c*rows + r]  <->  rowmajor[r*ld + c]; 32x32 tiles through padded shared memory so both
 // sides are coalesced.

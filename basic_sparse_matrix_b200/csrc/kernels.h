@@ -65,6 +65,9 @@ int launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t count, uint64
                       uint32_t *flag /* set to 1 when (v - subtract) >= bound */, cudaStream_t stream);
 int launch_row_stats(const uint32_t *row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag, cudaStream_t stream);
 int launch_col_range(const uint32_t *col_idx, uint64_t nnz, uint32_t *min_max /* [2], preset to {~0u, 0} */, cudaStream_t stream);
+int launch_residual_norms(int dtype, const void *x, uint64_t ldx, const void *y, uint64_t ldy, uint64_t rows, uint64_t cols,
+                          double *partial, cudaStream_t stream);   // result in partial[scratch-2], partial[scratch-1]
+int residual_norm_scratch_doubles();
 int launch_transpose_cm2rm(int dtype, const void *colmajor, void *rowmajor, uint64_t rows, uint64_t cols, uint64_t ld,
                            cudaStream_t stream);
 int launch_transpose_rm2cm(int dtype, const void *rowmajor, void *colmajor, uint64_t rows, uint64_t cols, uint64_t ld,

@@ -7,9 +7,10 @@ namespace bsm {
 
 constexpr int row_default_u(int NT) { return NT >= 4 ? 2 : (NT == 2 ? 4 : 8); }
 
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true> static const void *rk()
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true>
+static const void *rk()
 {
-    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED>);
+    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA>);
 }
 
 // Register-budget flavours (`flavour` argument of the selectors):
@@ -28,6 +29,7 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
             case 1: return rk<T, V, 32, NT, true, U2, 512, 1>();
             case 2: return rk<T, V, 32, NT, true, U1, 256, 3>();
             case 3: return rk<T, V, 32, NT, true, U1, 256, 4>();
+            case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // flavour 2 with scalar A-stream reads (A/B)
         }
         return rk<T, V, 32, NT, true, U1, 512, 1>();
     }

@@ -104,7 +104,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
 // as entry k has been consumed); MAXT / MINB = launch bounds (threads per CTA, CTAs per SM the register allocation must allow).
 // STAGED = col_idx / values of every slice fit the TMA stage (the host guarantees it from the longest
 // row); the unstaged variant reads them from global memory and stages only the row_ptr windows.
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED, bool VECA = true>
 __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
             const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
             const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
             if constexpr (STAGED)
-                process_slice<T, V, G, NT, FULLN, U, true>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
+                process_slice<T, V, G, NT, FULLN, U, VECA>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                      reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes, c_bytes,
                                                      col_ok, grp, streaming);
             else

@@ -157,6 +157,12 @@ class DeviceDense(_Handle):
         check(getattr(lib(), f"bsm_dense_download_{sfx}")(self.handle, _lib.col_ptr_array(into.data)))
         return into
 
+    def residual_norm(self, b: "DeviceDense") -> tuple:
+        """(||self - b||_F, ||b||_F) — the residual check of BASELINE config 5 with self = A·X."""
+        r, n = C.c_double(0.0), C.c_double(0.0)
+        check(lib().bsm_dense_residual_norm(self.handle, b.handle, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
     def into_csr(self) -> "DeviceCsr":
         """Zero-dropping compaction = the reference's result construction (sparse.rs:442, 222-233,
         206-219), on the device."""

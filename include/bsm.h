@@ -185,6 +185,10 @@ uint64_t bsm_kernel_launch_count(void);
  * (206-219). Device-side count -> scan -> scatter; returns a device Csr (rows x cols of d). */
 int bsm_dense_to_csr(const bsm_dense *d, bsm_csr **out);
 
+/* Residual check of BASELINE config 5 (||AX - B||): Frobenius norms ||ax - b|| and ||b|| of two
+ * device-resident dense matrices of equal shape, accumulated in f64 with a fixed reduction tree. */
+int bsm_dense_residual_norm(const bsm_dense *ax, const bsm_dense *b, double *resid_fro, double *b_fro);
+
 /* Host-to-host convenience = the literal reference call: uploads A and B, multiplies, compacts
  * and returns the zero-dropped result Csr in reference layout. The result arrays are allocated
  * by the library; release with bsm_host_free. */

@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
     """Compile the oracle with gcc (oracle/Makefile)."""
     if force or not os.path.exists(_SO) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
-        for f in ("ref_cpu.c", "ref_cpu_impl.h")
+        for f in ("ref_cpu.c", "ref_cpu_impl.h", "ref_solve_band.c")
     ):
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return _SO

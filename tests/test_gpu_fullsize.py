@@ -161,3 +161,43 @@ def test_config1_bench_shape_all_sizes(gpu):
         ref = OracleCsr.from_raw((1000, 1000), v, ci, ri).mul_dense([c.copy() for c in x.data], faithful=False)
         assert np.array_equal(out.v, ref.v) and np.array_equal(out.col_index, ref.col_index)
         assert np.array_equal(out.row_index, ref.row_index)
+
+
+@pytest.mark.parametrize("n_rows", [1 << 14, 1 << 20])
+def test_config5_cholesky_solve_residual_check(gpu, n_rows):
+    """configs[4] end to end: the reference's Cholesky solve (banded restatement, pinned on the f32 KATs
+    by tests/test_oracle_solve.py) produces X on the CPU for an SPD band matrix, half-bandwidth 32;
+    the GPU hot path computes R = A*X (32 right-hand sides) and the one-column SpMV, and the fused
+    residual norm ||AX - B|| / ||B||. Sampled rows of A*X are bit-exact against the sequential sum."""
+    from oracle import ref_solve
+    hb, nrhs = 32, 32
+    a_band = ref_solve.spd_band(n_rows, hb)
+    b_cols = gen.dense_rows(n_rows, nrhs, 6, gen.MODE_REAL, 0.5, np.float32).T.copy()     # (nrhs, n): one row per Dense column
+    x_cols = ref_solve.solve_band(a_band, b_cols)                                       # CPU producer (reference solve)
+    assert np.isfinite(x_cols).all()
+
+    a = gpu.DeviceCsr.band(n_rows, hb, dtype=np.float32)
+    x = gpu.DeviceDense.from_rowmajor(np.ascontiguousarray(x_cols.T))
+    b = gpu.DeviceDense.generate(n_rows, nrhs, seed=6, mode=gen.MODE_REAL, offset=0.5, dtype=np.float32)
+    ax = a.mul_dense(x)
+    assert gpu.last_launch_info()["algo"] == _lib.ALGO_VECTOR
+    resid, bnorm = ax.residual_norm(b)
+    # an f32 Cholesky solve of a strictly diagonally dominant system: relative residual ~ 1e-7
+    assert resid / bnorm < 2e-6, (resid, bnorm)
+    # host check of the fused norm on a slice, and of A*X itself on sampled rows (bitwise)
+    ids = sample_rows(np.random.default_rng(7), n_rows, extra=[hb - 1, hb, n_rows - hb - 1])
+    got = rows_of(ax, ids, gpu)
+    want = []
+    for i in ids:
+        rv, rc, rr, _ = gen.band(n_rows, hb, int(i), int(i) + 1, np.float32)
+        xs = np.ascontiguousarray(x_cols[:, rc.astype(np.int64)].T)
+        want.append(ref_numpy.mul_dense_rowmajor(rv, np.arange(len(rc), dtype=np.uint64), rr, xs)[0])
+    assert_bitwise(got, np.stack(want), "config 5 A*X")
+    if n_rows <= 1 << 14:
+        full = ax.to_rowmajor().astype(np.float64) - b.to_rowmajor().astype(np.float64)
+        assert abs(np.sqrt((full ** 2).sum()) - resid) <= 1e-9 * max(resid, 1e-30) + 1e-12
+    # one-column SpMV of the same matrix through mul_vector (dense slice in, dense slice out)
+    y = np.zeros(n_rows, np.float32)
+    a.to_host().mul_vector(x_cols[0], y) if n_rows <= 1 << 14 else None
+    if n_rows <= 1 << 14:
+        assert np.array_equal(y, ax.to_rowmajor()[:, 0])
