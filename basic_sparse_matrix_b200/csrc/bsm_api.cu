@@ -378,15 +378,19 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         if (user_R) {
             R = (uint32_t)tn.rows_per_slice;
         } else {
-            R = (uint32_t)std::min<double>(256.0, std::max(1.0, 128.0 / std::max(1.0, mean)));
+            // measured (profiles/r1_sweepi_*): one register tile per lane (NT = 1) likes ~224-entry slices
+            const double target = (sh.G == 32 && sh.NT == 1) ? 224.0 : 128.0;
+            R = (uint32_t)std::min<double>(256.0, std::max(1.0, target / std::max(1.0, mean)));
             if (sh.G < 32) R = std::max(R, 4u * rpp);
         }
         R = std::max(rq, R / rq * rq);
         // register-budget flavour (spmm_rows_inst.cuh); flavours 2 and 3 exist for full-width G == 32 shapes
         const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
-        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 5) - 1 : (wide_full && !user_nw ? 2 : 0);
-        if (!wide_full) flavour = 0;
-        if (flavour >= 2 && nw > 8) nw = 8;
+        // default for full-width shapes: 3 CTAs x 8 warps per SM; scalar A-stream reads when a lane holds several
+        // register tiles (measured 8 % faster at n = 128 f64), LDS.128 reads when it holds one
+        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 5) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 2) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
+        if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
+        if (flavour >= 2 && wide_full && nw > 8) nw = 8;
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
         p.flags = flags;
         // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start).
@@ -395,8 +399,8 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // hardware limit. If even the smallest slice cannot be staged, col_idx / values are read from
         // global memory instead (unstaged variant).
         const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
-        const int resident = (flavour == 2 || flavour == 4) ? 3 : (flavour == 3 ? 4 : 1);
-        const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (128 * 1024) / resident);
+        const int resident = (flavour == 2 || (flavour == 4 && wide_full)) ? 3 : (flavour == 3 ? 4 : 1);
+        const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (160 * 1024) / resident);
         const uint32_t window = (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight (U)
         p.R = R;
         auto smem_now = [&]() {
@@ -424,6 +428,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // rows per warp inside a super-batch: the dominant row stride of a stencil-like matrix (so the
         // warps of a CTA sweep adjacent lines), else one slice
         uint32_t P = R;
+        if (tn.rows_per_warp <= 0 && sh.G < 32 && a->rows / ((uint64_t)nw * 4 * R) >= 4ull * g_rt.sm_count) P = 4 * R;   // measured: band x 32
         if (tn.rows_per_warp > 0) {
             P = (uint32_t)tn.rows_per_warp;
         } else if (a->row_stride >= 2 * R) {

@@ -18,6 +18,7 @@ static const void *rk()
 //   1: same, gather window twice as deep
 //   2: CTAs of up to 256 threads, 3 per SM (<= 85 registers)
 //   3: CTAs of up to 256 threads, 4 per SM (<= 64 registers)
+//   4: flavour 2 with scalar (one LDS per entry) instead of LDS.128 reads of col_idx / values
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
 // G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
 template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int flavour)
@@ -29,7 +30,7 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
             case 1: return rk<T, V, 32, NT, true, U2, 512, 1>();
             case 2: return rk<T, V, 32, NT, true, U1, 256, 3>();
             case 3: return rk<T, V, 32, NT, true, U1, 256, 4>();
-            case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // flavour 2 with scalar A-stream reads (A/B)
+            case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // flavour 2 with scalar A-stream reads
         }
         return rk<T, V, 32, NT, true, U1, 512, 1>();
     }
@@ -39,6 +40,7 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
 template <typename T, int V, int G> static const void *rk_narrow(bool fulln, int flavour)
 {
     if (flavour < 0) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, false>() : rk<T, V, G, 1, false, 8, 512, 1, false>();
+    if (flavour == 4) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, false>() : rk<T, V, G, 1, false, 8, 512, 1, true, false>();   // scalar A reads
     return fulln ? rk<T, V, G, 1, true, 8, 512, 1>() : rk<T, V, G, 1, false, 8, 512, 1>();
 }
 

@@ -91,7 +91,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             Lane<T, V> acc[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) acc[t].zero();
-            stream_entries<T, V, NT, FULLN, U, false, false>(ci, va, s, e, b_bytes, ldb_bytes, col_ok, G, acc, [](uint32_t) {});
+            stream_entries<T, V, NT, FULLN, U, VECA, false>(ci, va, s, e, b_bytes, ldb_bytes, col_ok, G, acc, [](uint32_t) {});
             T *crow = reinterpret_cast<T *>(c_bytes + (size_t)(row0 + r) * ldc_bytes);
 #pragma unroll
             for (int t = 0; t < NT; ++t)

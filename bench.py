@@ -190,6 +190,41 @@ def time_device_steps(torch, A, B, C, steps, warmup, tuning=None, barrier=None):
     return total_ms, per
 
 
+def run_config1(torch, gpu, peak, e=900_000):
+    """BASELINE configs[0]: the reference's own `sd_mul` bench shape (benches/sparse_dense_mul.rs:6-35,
+    f64 for u32): 1000x1000 Csr built by `e` unordered inserts x Dense 1000x10. Small enough for the CPU
+    port to run IN FULL beside the GPU: device-resident kernel time, the literal host call
+    (`Csr.mul_dense` -> zero-dropped Csr, uploads and download included) and the CPU restatement."""
+    from basic_sparse_matrix_b200 import gen
+    from oracle.ref_cpu import OracleCsr
+    a, x = gen.bench_as_written(e)
+    v, ci, ri = a.raw_parts()
+    A = gpu.DeviceCsr.from_host(a)
+    B = gpu.DeviceDense.from_host(x)
+    C = gpu.DeviceDense.alloc(1000, 10, np.float64)
+    total_ms, per = time_device_steps(torch, A, B, C, 20, 3)
+    info = gpu.last_launch_info()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        out = a.mul_dense(x)
+    t_host = (time.perf_counter() - t0) / 5
+    o = OracleCsr.from_raw((1000, 1000), v, ci, ri)
+    cols = [np.ascontiguousarray(c) for c in x.data]
+    t_cpu = min(o.time_mul_dense_rows(cols, 0, 1000, faithful=True)[0] for _ in range(3))
+    ref = o.mul_dense(cols, faithful=False)
+    same = bool(np.array_equal(out.v, ref.v) and np.array_equal(out.col_index, ref.col_index) and np.array_equal(out.row_index, ref.row_index))
+    nnz = int(ri[-1])
+    for h in (A, B, C):
+        h.close()
+    return {"workload": f"bench_as_written_e{e}_n10_f64", "rows": 1000, "nnz": nnz, "n": 10, "dtype": "f64",
+            "algo": "merge" if info["algo"] == 2 else "vector", "ms_per_step": round(total_ms / 20, 4), "ms_best": round(min(per), 4),
+            "gflops": round(2.0 * nnz * 10 / (total_ms / 20 * 1e-3) / 1e9, 2), "kernels_per_step": info["kernels"],
+            "host_call_ms": round(t_host * 1e3, 3), "host_call_gflops": round(2.0 * nnz * 10 / t_host / 1e9, 3),
+            "cpu_port_ms_full": round(t_cpu * 1e3, 3), "cpu_port_gflops": round(2.0 * nnz * 10 / t_cpu / 1e9, 4),
+            "result_csr_equals_cpu_port": same,
+            "note": "launch-bound on the GPU (11 MB of operands); the one config the CPU port runs in full"}
+
+
 def run_extra(torch, gpu, name, steps, warmup, peak):
     """Secondary single-GPU workloads (kernel-only numbers, reported under other_workloads)."""
     from basic_sparse_matrix_b200 import gen
@@ -496,6 +531,10 @@ def main():
                 extras.append(run_extra(torch, gpu, name, 10, 3, peak))
             except Exception as ex:   # keep the headline line even if a side workload fails
                 extras.append({"workload": name, "error": str(ex)[:200]})
+        try:
+            extras.append(run_config1(torch, gpu, peak))
+        except Exception as ex:
+            extras.append({"workload": "bench_as_written", "error": str(ex)[:200]})
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 1), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
