@@ -432,9 +432,24 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         if (tn.rows_per_warp > 0) {
             P = (uint32_t)tn.rows_per_warp;
         } else if (a->row_stride >= 2 * R) {
-            P = a->row_stride;
-            // enough super-batches to keep every SM busy: P = stride / m keeps warps w and w+m adjacent
-            while (P % 2 == 0 && P / 2 >= 2 * R && a->rows / ((uint64_t)nw * P) < 4ull * g_rt.sm_count) P /= 2;
+            // P = stride / m keeps warps w and w+m on adjacent lines. Among stride, stride/2, stride/4, ...
+            // pick the one that wastes least to wave quantisation (rounds x rows per warp per round); a
+            // larger P wins unless a smaller one saves more than 10 % (measured on 1/8 and 1/4 row blocks:
+            // profiles/r1_sweepk_l3d_n128_s8.jsonl — locality beats balance). Too few rows for even one
+            // round per SM: fall back to plain slices.
+            const uint64_t grid_est = (uint64_t)g_rt.sm_count * resident;
+            double best_cost = 0.0;
+            uint32_t best_p = 0;
+            for (uint32_t cand = a->row_stride; cand >= 2 * R; cand /= 2) {
+                const uint64_t supers = (a->rows + (uint64_t)nw * cand - 1) / ((uint64_t)nw * cand);
+                const double cost = (double)((supers + grid_est - 1) / grid_est) * cand;
+                if (best_p == 0 || cost < 0.90 * best_cost) {
+                    best_cost = cost;
+                    best_p = cand;
+                }
+                if (cand % 2) break;
+            }
+            P = best_p ? best_p : R;
             if (a->rows / ((uint64_t)nw * P) < (uint64_t)g_rt.sm_count) P = R;
         }
         P = std::max(R, (P + R - 1) / R * R);

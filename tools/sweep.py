@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--points", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--slice", default="", help="p/N: time rank p's nnz-balanced row block of an N-way partition on this one GPU")
     args = ap.parse_args()
 
     import torch
@@ -51,7 +52,12 @@ def main():
     kind, prm, n, dt = bench.WORKLOADS[args.workload]
     dtype = bench.NP_DTYPE[dt]
     s = np.dtype(dtype).itemsize
-    A = bench.make_device_csr(gpu, kind, prm, dtype)
+    if args.slice:
+        pnum, nparts = (int(x) for x in args.slice.split("/"))
+        bounds = gpu.partition_rows(bench.host_row_index(kind, prm), nparts).astype(np.int64)
+        A = bench.make_device_csr(gpu, kind, prm, dtype, int(bounds[pnum]), int(bounds[pnum + 1]))
+    else:
+        A = bench.make_device_csr(gpu, kind, prm, dtype)
     ai = A.info()
     B = gpu.DeviceDense.generate(ai["cols"], n, seed=5, mode=gen.MODE_EXACT, dtype=dtype)
     C = gpu.DeviceDense.alloc(ai["rows"], n, dtype)
