@@ -33,10 +33,40 @@ int ensure_init()
     return bsm_init(0);
 }
 
-static int dev_alloc(void **p, size_t bytes)
+// Two kinds of device memory:
+//   * long-lived handles created by the public upload / alloc / generator calls: cudaMalloc;
+//   * temporaries, and the handles the host-to-host convenience calls create and destroy inside one
+//     call (PoolScope): the stream-ordered pool of the device, kept warm (release threshold = max), so
+//     that a small multiplication does not pay a dozen cudaMalloc / cudaFree round trips.
+static thread_local int g_pool_depth = 0;
+struct PoolScope {
+    PoolScope() { ++g_pool_depth; }
+    ~PoolScope() { --g_pool_depth; }
+};
+
+static int tmp_alloc(void **p, size_t bytes)
 {
+    BSM_CUDA(cudaMallocAsync(p, bytes ? bytes : 16, g_rt.stream));
+    return BSM_OK;
+}
+static void tmp_free(void *p)
+{
+    if (p) cudaFreeAsync(p, g_rt.stream);
+}
+static int dev_alloc(void **p, size_t bytes, bool *pooled)
+{
+    *pooled = g_pool_depth > 0;
+    if (*pooled) return tmp_alloc(p, bytes);
     BSM_CUDA(cudaMalloc(p, bytes ? bytes : 16));
     return BSM_OK;
+}
+static void dev_free(void *p, bool pooled)
+{
+    if (!p) return;
+    if (pooled)
+        cudaFreeAsync(p, g_rt.stream);
+    else
+        cudaFree(p);
 }
 
 static inline uint64_t pad4(uint64_t n) { return (n + 3) / 4 * 4; }
@@ -60,9 +90,9 @@ static int alloc_csr(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, bsm_
     a->cols = cols;
     a->nnz = nnz;
     const size_t s = dtype_size(dtype);
-    int st = dev_alloc(&a->vals, (pad4(nnz) + 4) * s);
-    if (st == BSM_OK) st = dev_alloc((void **)&a->col_idx, (pad4(nnz) + 4) * 4);
-    if (st == BSM_OK) st = dev_alloc((void **)&a->row_ptr, (pad4(rows + 1) + 4) * 4);
+    int st = dev_alloc(&a->vals, (pad4(nnz) + 4) * s, &a->pooled);
+    if (st == BSM_OK) st = dev_alloc((void **)&a->col_idx, (pad4(nnz) + 4) * 4, &a->pooled);
+    if (st == BSM_OK) st = dev_alloc((void **)&a->row_ptr, (pad4(rows + 1) + 4) * 4, &a->pooled);
     if (st != BSM_OK) {
         bsm_csr_free(a);
         return st;
@@ -148,8 +178,8 @@ static int csr_upload_rows(int dtype, uint64_t rows_total, uint64_t cols, const 
     const uint64_t stage_elems = std::max<uint64_t>(nnz, rows + 1);
     int st = BSM_OK;
     auto body = [&]() -> int {
-        BSM_CUDA(cudaMalloc(&stage, stage_elems * 8));
-        BSM_CUDA(cudaMalloc(&flags, 8));
+        BSM_TRY(tmp_alloc((void **)&stage, stage_elems * 8));
+        BSM_TRY(tmp_alloc((void **)&flags, 8));
         BSM_CUDA(cudaMemsetAsync(flags, 0, 8, sm));
         if (nnz) {
             BSM_CUDA(cudaMemcpyAsync(a->vals, v + e0, nnz * sizeof(T), cudaMemcpyHostToDevice, sm));
@@ -167,8 +197,8 @@ static int csr_upload_rows(int dtype, uint64_t rows_total, uint64_t cols, const 
         return compute_stats(a);
     };
     st = body();
-    if (stage) cudaFree(stage);
-    if (flags) cudaFree(flags);
+    tmp_free(stage);
+    tmp_free(flags);
     if (st != BSM_OK) {
         bsm_csr_free(a);
         return st;
@@ -199,7 +229,7 @@ template <typename T> static int csr_download(const bsm_csr *a, int dtype, T *v,
     cudaStream_t sm = g_rt.stream;
     uint64_t *stage = nullptr;
     const uint64_t stage_elems = std::max<uint64_t>(a->nnz, a->rows + 1);
-    BSM_CUDA(cudaMalloc(&stage, stage_elems * 8));
+    BSM_TRY(tmp_alloc((void **)&stage, stage_elems * 8));
     int st = [&]() -> int {
         if (a->nnz) {
             BSM_CUDA(cudaMemcpyAsync(v, a->vals, a->nnz * sizeof(T), cudaMemcpyDeviceToHost, sm));
@@ -211,7 +241,7 @@ template <typename T> static int csr_download(const bsm_csr *a, int dtype, T *v,
         BSM_CUDA(cudaStreamSynchronize(sm));
         return BSM_OK;
     }();
-    cudaFree(stage);
+    tmp_free(stage);
     return st;
 }
 
@@ -227,7 +257,7 @@ static int dense_alloc(int dtype, uint64_t rows, uint64_t cols, bsm_dense **out)
     d->cols = cols;
     d->ld = default_ld(cols, dtype);
     const size_t bytes = (size_t)rows * d->ld * dtype_size(dtype);
-    int st = dev_alloc(&d->data, bytes + 16);
+    int st = dev_alloc(&d->data, bytes + 16, &d->pooled);
     if (st != BSM_OK) {
         delete d;
         return st;
@@ -250,7 +280,7 @@ template <typename T> static int dense_upload(int dtype, uint64_t rows, uint64_t
     int st = [&]() -> int {
         if (rows == 0 || cols == 0) return BSM_OK;
         const uint64_t g = std::min<uint64_t>(kColGroup, cols);
-        BSM_CUDA(cudaMalloc(&stage, g * rows * sizeof(T)));
+        BSM_TRY(tmp_alloc((void **)&stage, g * rows * sizeof(T)));
         for (uint64_t c0 = 0; c0 < cols; c0 += g) {
             const uint64_t gc = std::min<uint64_t>(g, cols - c0);
             for (uint64_t c = 0; c < gc; ++c) {
@@ -263,7 +293,7 @@ template <typename T> static int dense_upload(int dtype, uint64_t rows, uint64_t
         BSM_CUDA(cudaStreamSynchronize(sm));
         return BSM_OK;
     }();
-    if (stage) cudaFree(stage);
+    tmp_free(stage);
     if (st != BSM_OK) {
         bsm_dense_free(d);
         return st;
@@ -282,7 +312,7 @@ template <typename T> static int dense_download(const bsm_dense *d, int dtype, T
     cudaStream_t sm = g_rt.stream;
     T *stage = nullptr;
     const uint64_t g = std::min<uint64_t>(kColGroup, d->cols);
-    BSM_CUDA(cudaMalloc(&stage, g * d->rows * sizeof(T)));
+    BSM_TRY(tmp_alloc((void **)&stage, g * d->rows * sizeof(T)));
     int st = [&]() -> int {
         for (uint64_t c0 = 0; c0 < d->cols; c0 += g) {
             const uint64_t gc = std::min<uint64_t>(g, d->cols - c0);
@@ -293,7 +323,7 @@ template <typename T> static int dense_download(const bsm_dense *d, int dtype, T
         }
         return BSM_OK;
     }();
-    cudaFree(stage);
+    tmp_free(stage);
     return st;
 }
 
@@ -480,12 +510,21 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
     return BSM_OK;
 }
 
+// merge-path caches of a handle live where the handle's arrays live (pool or cudaMalloc); all of one kind
+static int cache_alloc(bsm_csr *a, void **p, size_t bytes)
+{
+    if (!a->part_rows && !a->carry_vals && !a->long_rows) a->cache_pooled = a->pooled && a->owns;
+    if (a->cache_pooled) return tmp_alloc(p, bytes);
+    BSM_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    return BSM_OK;
+}
+
 static int ensure_partition(bsm_csr *a, uint32_t items, uint32_t num_chunks)
 {
     if (a->part_rows && a->part_items == (int)items && a->part_chunks == num_chunks) return BSM_OK;
-    if (a->part_rows) cudaFree(a->part_rows);
+    dev_free(a->part_rows, a->cache_pooled);
     a->part_rows = nullptr;
-    BSM_CUDA(cudaMalloc(&a->part_rows, ((size_t)num_chunks + 1) * 4));
+    BSM_TRY(cache_alloc(a, (void **)&a->part_rows, ((size_t)num_chunks + 1) * 4));
     BSM_TRY(launch_merge_partition(a->row_ptr, (uint32_t)a->rows, (uint32_t)a->nnz, items, num_chunks, a->part_rows, g_rt.stream));
     g_info.kernels += 1;
     a->part_items = (int)items;
@@ -521,19 +560,19 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
         BSM_TRY(ensure_partition(a, items, num_chunks));
         const size_t need_vals = (size_t)num_chunks * ldcar * s;
         if (a->carry_vals_bytes < need_vals) {
-            if (a->carry_vals) cudaFree(a->carry_vals);
+            dev_free(a->carry_vals, a->cache_pooled);
             a->carry_vals = nullptr;
             a->carry_vals_bytes = 0;
-            BSM_CUDA(cudaMalloc(&a->carry_vals, need_vals));
+            BSM_TRY(cache_alloc(a, &a->carry_vals, need_vals));
             a->carry_vals_bytes = need_vals;
         }
         // rows whose run of carries exceeds 64 chunks need more than 64*items entries: at most this many
         const uint64_t long_cap = a->nnz / (64ull * items) + 1;
         if (a->long_rows_cap < long_cap) {
-            if (a->long_rows) cudaFree(a->long_rows);
+            dev_free(a->long_rows, a->cache_pooled);
             a->long_rows = nullptr;
             a->long_rows_cap = 0;
-            BSM_CUDA(cudaMalloc(&a->long_rows, (2 * long_cap + 1) * 4));
+            BSM_TRY(cache_alloc(a, (void **)&a->long_rows, (2 * long_cap + 1) * 4));
             a->long_rows_cap = long_cap;
         }
         MergeParams p{};
@@ -615,8 +654,8 @@ static int dense_to_csr_impl(const bsm_dense *d, bsm_csr **out)
     unsigned long long *total = nullptr;
     bsm_csr *r = nullptr;
     int st = [&]() -> int {
-        BSM_CUDA(cudaMalloc(&counts, (pad4(d->rows + 1) + 4) * 4));
-        BSM_CUDA(cudaMalloc(&total, 8));
+        BSM_TRY(tmp_alloc((void **)&counts, (pad4(d->rows + 1) + 4) * 4));
+        BSM_TRY(tmp_alloc((void **)&total, 8));
         BSM_CUDA(cudaMemsetAsync(total, 0, 8, sm));
         BSM_CUDA(cudaMemsetAsync(counts, 0, (pad4(d->rows + 1) + 4) * 4, sm));
         BSM_TRY(launch_count_nonzero(d->dtype, d->data, d->rows, d->cols, d->ld, counts, total, sm));
@@ -631,8 +670,8 @@ static int dense_to_csr_impl(const bsm_dense *d, bsm_csr **out)
         BSM_CUDA(cudaStreamSynchronize(sm));
         return BSM_OK;
     }();
-    if (counts) cudaFree(counts);
-    if (total) cudaFree(total);
+    tmp_free(counts);
+    tmp_free(total);
     if (st != BSM_OK) {
         if (r) bsm_csr_free(r);
         return st;
@@ -648,6 +687,8 @@ static int mul_dense_host(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz,
                           uint64_t **out_row_index)
 {
     if (!out_nnz || !out_v || !out_col_index || !out_row_index) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense_host: null out");
+    BSM_TRY(ensure_init());
+    PoolScope pool;
     if (cols != rhs_rows) return fail(BSM_ERR_INCORRECT_DIMENSIONS, "mul_dense: A.cols != rhs.rows (MatErr::IncorrectDimensions)");
     bsm_csr *a = nullptr, *r = nullptr;
     bsm_dense *b = nullptr, *c = nullptr;
@@ -694,6 +735,8 @@ static int mul_dense_host_dense(int dtype, uint64_t rows, uint64_t cols, uint64_
 {
     if (cols != rhs_rows) return fail(BSM_ERR_INCORRECT_DIMENSIONS, "mul_dense: A.cols != rhs.rows (MatErr::IncorrectDimensions)");
     if (rhs_cols && (!rhs_col_ptrs || !out_col_ptrs)) return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense_host_dense: null column pointers");
+    BSM_TRY(ensure_init());
+    PoolScope pool;
     bsm_csr *a = nullptr;
     BSM_TRY(csr_upload<T>(dtype, rows, cols, nnz, v, col_index, row_index, row_index_len, &a));
     if (rows == 0 || rhs_cols == 0) {
@@ -718,11 +761,17 @@ static int mul_dense_host_dense(int dtype, uint64_t rows, uint64_t cols, uint64_
             BSM_CUDA(cudaEventCreateWithFlags(&ev_in_free[i], cudaEventDisableTiming));
             BSM_CUDA(cudaEventCreateWithFlags(&ev_c[i], cudaEventDisableTiming));
             BSM_CUDA(cudaEventCreateWithFlags(&ev_out_free[i], cudaEventDisableTiming));
-            BSM_CUDA(cudaMalloc(&stage_in[i], w * rhs_rows * sizeof(T)));
-            BSM_CUDA(cudaMalloc(&bg[i], w * rhs_rows * sizeof(T) + 16));
-            BSM_CUDA(cudaMalloc(&cg[i], w * rows * sizeof(T) + 16));
-            BSM_CUDA(cudaMalloc(&stage_out[i], w * rows * sizeof(T)));
+            BSM_TRY(tmp_alloc((void **)&stage_in[i], w * rhs_rows * sizeof(T)));
+            BSM_TRY(tmp_alloc((void **)&bg[i], w * rhs_rows * sizeof(T) + 16));
+            BSM_TRY(tmp_alloc((void **)&cg[i], w * rows * sizeof(T) + 16));
+            BSM_TRY(tmp_alloc((void **)&stage_out[i], w * rows * sizeof(T)));
         }
+        // the pool hands the buffers out in the order of the library stream: make the three pipeline
+        // streams wait for that point
+        BSM_CUDA(cudaEventRecord(ev_in_free[0], user_stream));
+        BSM_CUDA(cudaStreamWaitEvent(s_in, ev_in_free[0], 0));
+        BSM_CUDA(cudaStreamWaitEvent(s_mm, ev_in_free[0], 0));
+        BSM_CUDA(cudaStreamWaitEvent(s_out, ev_in_free[0], 0));
         for (uint64_t g = 0; g < ngroups; ++g) {
             const int i = (int)(g & 1);
             const uint64_t c0 = g * w, gc = std::min<uint64_t>(w, rhs_cols - c0);
@@ -769,10 +818,10 @@ static int mul_dense_host_dense(int dtype, uint64_t rows, uint64_t cols, uint64_
     g_rt.stream = user_stream;
     if (st != BSM_OK) cudaDeviceSynchronize();   // nothing may still be using the buffers freed below
     for (int i = 0; i < 2; ++i) {
-        if (stage_in[i]) cudaFree(stage_in[i]);
-        if (stage_out[i]) cudaFree(stage_out[i]);
-        if (bg[i]) cudaFree(bg[i]);
-        if (cg[i]) cudaFree(cg[i]);
+        tmp_free(stage_in[i]);
+        tmp_free(stage_out[i]);
+        tmp_free(bg[i]);
+        tmp_free(cg[i]);
         if (ev_in[i]) cudaEventDestroy(ev_in[i]);
         if (ev_in_free[i]) cudaEventDestroy(ev_in_free[i]);
         if (ev_c[i]) cudaEventDestroy(ev_c[i]);
@@ -795,6 +844,7 @@ static int mul_vector(const bsm_csr *a, int dtype, const T *rhs, uint64_t rhs_le
     if (a->cols != rhs_len || a->rows != out_len)
         return fail(BSM_ERR_INCORRECT_DIMENSIONS, "mul_vector: dims (MatErr::IncorrectDimensions)");
     bsm_dense *x = nullptr, *y = nullptr;
+    PoolScope pool;
     int st = [&]() -> int {
         BSM_TRY(dense_alloc(dtype, rhs_len, 1, &x));
         BSM_TRY(dense_alloc(dtype, out_len, 1, &y));
@@ -820,7 +870,7 @@ static int gen_counted(int dtype, uint64_t rows, uint64_t cols, CountFn count_fn
     uint32_t *counts = nullptr;
     bsm_csr *a = nullptr;
     int st = [&]() -> int {
-        BSM_CUDA(cudaMalloc(&counts, (rows + 1) * 4 + 16));
+        BSM_TRY(tmp_alloc((void **)&counts, (rows + 1) * 4 + 16));
         BSM_CUDA(cudaMemsetAsync(counts, 0, (rows + 1) * 4 + 16, sm));
         BSM_TRY(count_fn(counts, sm));
         BSM_TRY(exclusive_scan_u32(counts, counts, rows + 1, sm));
@@ -832,7 +882,7 @@ static int gen_counted(int dtype, uint64_t rows, uint64_t cols, CountFn count_fn
         BSM_TRY(fill_fn(a, sm));
         return compute_stats(a);
     }();
-    if (counts) cudaFree(counts);
+    tmp_free(counts);
     if (st != BSM_OK) {
         if (a) bsm_csr_free(a);
         return st;
@@ -889,6 +939,11 @@ int bsm_init(int device)
     g_rt.cc_major = prop.major;
     g_rt.cc_minor = prop.minor;
     g_rt.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+        unsigned long long keep = ~0ull;   // never trim the stream-ordered pool behind our back
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     return BSM_OK;
 }
 
@@ -1000,13 +1055,13 @@ int bsm_csr_free(bsm_csr *a)
 {
     if (!a) return BSM_OK;
     if (a->owns) {
-        if (a->vals) cudaFree(a->vals);
-        if (a->col_idx) cudaFree(a->col_idx);
-        if (a->row_ptr) cudaFree(a->row_ptr);
+        dev_free(a->vals, a->pooled);
+        dev_free(a->col_idx, a->pooled);
+        dev_free(a->row_ptr, a->pooled);
     }
-    if (a->part_rows) cudaFree(a->part_rows);
-    if (a->carry_vals) cudaFree(a->carry_vals);
-    if (a->long_rows) cudaFree(a->long_rows);
+    dev_free(a->part_rows, a->cache_pooled);
+    dev_free(a->carry_vals, a->cache_pooled);
+    dev_free(a->long_rows, a->cache_pooled);
     delete a;
     return BSM_OK;
 }
@@ -1070,7 +1125,7 @@ int bsm_dense_borrow(int dtype, uint64_t rows, uint64_t cols, void *d_rowmajor, 
 int bsm_dense_free(bsm_dense *d)
 {
     if (!d) return BSM_OK;
-    if (d->owns && d->data) cudaFree(d->data);
+    if (d->owns) dev_free(d->data, d->pooled);
     delete d;
     return BSM_OK;
 }
@@ -1148,7 +1203,7 @@ int bsm_dense_residual_norm(const bsm_dense *ax, const bsm_dense *b, double *res
     if (ax->dtype != b->dtype) return fail(BSM_ERR_DTYPE_MISMATCH, "residual_norm: dtype mismatch");
     const int nd = residual_norm_scratch_doubles();
     double *d = nullptr;
-    BSM_CUDA(cudaMalloc(&d, nd * sizeof(double)));
+    BSM_TRY(tmp_alloc((void **)&d, nd * sizeof(double)));
     int st = launch_residual_norms(ax->dtype, ax->data, ax->ld, b->data, b->ld, ax->rows, ax->cols, d, g_rt.stream);
     double h[2] = {0.0, 0.0};
     if (st == BSM_OK) {
@@ -1156,7 +1211,7 @@ int bsm_dense_residual_norm(const bsm_dense *ax, const bsm_dense *b, double *res
         if (e == cudaSuccess) e = cudaStreamSynchronize(g_rt.stream);
         if (e != cudaSuccess) st = fail(BSM_ERR_CUDA, std::string("residual_norm: ") + cudaGetErrorString(e));
     }
-    cudaFree(d);
+    tmp_free(d);
     if (st != BSM_OK) return st;
     *resid_fro = std::sqrt(h[0]);
     *b_fro = std::sqrt(h[1]);

@@ -59,6 +59,8 @@ struct bsm_csr {
     uint32_t *col_idx = nullptr;   // u32[nnz]
     uint32_t *row_ptr = nullptr;   // u32[rows+1]
     bool owns = true;
+    bool pooled = false;           // arrays come from the stream-ordered pool (freed with cudaFreeAsync)
+    bool cache_pooled = false;     // likewise for the merge-path caches below
     uint64_t max_row_nnz = 0;      // csr_row_stats (dispatch heuristic)
     uint32_t col_min = 0, col_max = 0;   // smallest / largest stored column (valid when nnz > 0)
     uint32_t row_stride = 0;       // dominant off-diagonal column stride of a stencil-like matrix (0 = none)
@@ -78,6 +80,7 @@ struct bsm_dense {
     uint64_t rows = 0, cols = 0, ld = 0;
     void *data = nullptr;
     bool owns = true;
+    bool pooled = false;
 };
 
 // ------------------------------------------------------------------------------------------
