@@ -201,3 +201,28 @@ def test_config5_cholesky_solve_residual_check(gpu, n_rows):
     a.to_host().mul_vector(x_cols[0], y) if n_rows <= 1 << 14 else None
     if n_rows <= 1 << 14:
         assert np.array_equal(y, ax.to_rowmajor()[:, 0])
+
+
+def test_config4_checksum_of_checksums_full(gpu):
+    """Size-independent property at FULL size (256^3 Laplacian x 64 columns, exact dyadic data, so every
+    product and sum below is exact in f64 and the comparison is bitwise):
+        1^T (A B)  ==  (1^T A) B
+    The left side sums all 16.7 M rows of the vector kernel's product; both reductions are themselves run
+    as one-row CSR x dense products, i.e. through the merge-path kernel on a 16.7 M-entry row."""
+    g, n = 256, 64
+    rows = g ** 3
+    a = gpu.DeviceCsr.laplacian(g, g, g)
+    b = gpu.DeviceDense.generate(rows, n, seed=5, mode=gen.MODE_EXACT)
+    c = a.mul_dense(b)
+    assert gpu.last_launch_info()["algo"] == _lib.ALGO_VECTOR
+    ones_row = Csr.from_raw_parts((1, rows), np.ones(rows), np.arange(rows, dtype=np.uint64), np.array([0, rows], np.uint64))
+    d_ones = gpu.DeviceCsr.from_host(ones_row)
+    lhs = d_ones.mul_dense(c).to_rowmajor()                      # 1^T (A B)
+    assert gpu.last_launch_info()["algo"] == _lib.ALGO_MERGE
+    # 1^T A: the Laplacian is symmetric, so column sums = row sums = 6 - (number of neighbours)
+    colsum = 6.0 - (gen.laplacian_row_counts(g, g, g) - 1).astype(np.float64)
+    nzc = np.nonzero(colsum)[0].astype(np.uint64)                # interior points sum to 0 and are not stored
+    colsum_row = Csr.from_raw_parts((1, rows), colsum[nzc.astype(np.int64)], nzc, np.array([0, len(nzc)], np.uint64))
+    rhs = gpu.DeviceCsr.from_host(colsum_row).mul_dense(b).to_rowmajor()   # (1^T A) B
+    assert_bitwise(lhs, rhs, "checksum of checksums")
+    assert np.abs(lhs).max() > 0
