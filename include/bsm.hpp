@@ -7,8 +7,10 @@
 //     reference (Rust)                                     here (C++)
 //     util::MatDim / MatErr / GetDims   util.rs:11-55      sparse_matrix::MatDim / MatErr / get_dims()
 //     dense::Dense<T>                   dense.rs:4-47      sparse_matrix::Dense<T>
+//     dense_static::DenseS<T,R,C>       dense_static.rs    sparse_matrix::DenseS<T,R,C>
 //     sparse::Csr<T>, CsrEntry          sparse.rs:68-265   sparse_matrix::Csr<T>, CsrEntry<T>
 //     Csr::mul_dense                    sparse.rs:426-446  Csr<T>::mul_dense  (runs on the B200)
+//     Csr::mul_dense_s                  sparse.rs:448-466  Csr<T>::mul_dense_s (runs on the B200)
 //     Csr::mul_vector                   sparse.rs:468-482  Csr<T>::mul_vector (runs on the B200)
 //     new `gpu` module                    sparse_matrix::gpu::DeviceCsr<T> / DeviceDense<T>
 //
@@ -18,6 +20,7 @@
 // There is no CPU implementation of the multiplications here: without libbsm_b200 + a GPU they fail.
 #pragma once
 
+#include <array>
 #include <cstddef>
 #include <cstdint>
 #include <stdexcept>
@@ -170,6 +173,31 @@ template <typename T> class Dense {   // dense.rs:4-9 — COLUMN-major Vec<Vec<T
     std::vector<std::vector<T>> &columns_mut() { return data_; }
 };
 
+// ---- dense_static.rs --------------------------------------------------------------------------------
+template <typename T, std::size_t ROWS, std::size_t COLS> class DenseS {   // dense_static.rs:4-9 — [[T; ROWS]; COLS], column-major
+    std::array<std::array<T, ROWS>, COLS> data_;
+
+  public:
+    static DenseS new_default() { return new_(T()); }                            // dense_static.rs:13-15
+    static DenseS new_(T val)                                                    // dense_static.rs:17-19 (`new` is a C++ keyword)
+    {
+        DenseS d;
+        for (auto &c : d.data_) c.fill(val);
+        return d;
+    }
+    static DenseS from_data(const std::vector<std::vector<T>> &columns)          // dense_static.rs:21-35 — data[c] is COLUMN c
+    {
+        DenseS d = new_default();
+        for (std::size_t i = 0; i < COLS; ++i)
+            for (std::size_t j = 0; j < ROWS; ++j) d.data_[i][j] = columns.at(i).at(j);
+        return d;
+    }
+    const std::array<T, ROWS> &get_col(std::size_t col_index) const { return data_.at(col_index); }   // dense_static.rs:37-39
+    std::array<T, ROWS> &get_col_mut(std::size_t col_index) { return data_.at(col_index); }           // dense_static.rs:41-43
+    MatDim get_dims() const { return MatDim(ROWS, COLS); }                                            // dense_static.rs:46-53
+    bool operator==(const DenseS &o) const { return data_ == o.data_; }
+};
+
 // ---- sparse.rs ------------------------------------------------------------------------------------
 template <typename T> struct CsrEntry {   // sparse.rs:80-85
     T v;
@@ -278,6 +306,15 @@ template <typename T> class Csr {   // sparse.rs:68-78
     // same product with a DENSE result in the reference's column-major layout (no zero-drop): one pipelined
     // host-to-host call (H2D | multiply | D2H overlapped per column group)
     Result<Dense<T>> mul_dense_into_dense(const Dense<T> &rhs) const;
+    // Csr::mul_dense_s(&self, rhs:&DenseS<T,ROWS,COLS>) -> Result<Csr<T>,MatErr>  sparse.rs:448-466 — the same
+    // loop nest against the stack-array operand; same kernels
+    template <std::size_t ROWS, std::size_t COLS> Result<Csr> mul_dense_s(const DenseS<T, ROWS, COLS> &rhs) const
+    {
+        if (dims_.cols != ROWS) return Result<Csr>(MatErr::IncorrectDimensions);   // sparse.rs:449
+        std::vector<std::vector<T>> cols;
+        for (std::size_t c = 0; c < COLS; ++c) cols.emplace_back(rhs.get_col(c).begin(), rhs.get_col(c).end());
+        return mul_dense(Dense<T>::from_data(cols));
+    }
     // Csr::mul_vector(&self, rhs:&[T], out:&mut [T]) -> Result<(),MatErr>  sparse.rs:468-482
     Result<void> mul_vector(const std::vector<T> &rhs, std::vector<T> &out) const;
 };

@@ -68,6 +68,11 @@ template <typename T> static void structure_tests()
     Dense<T> d2 = Dense<T>::from_data({{1, 2, 3}, {4, 5, 6}, {7, 8, 9}});
     CHECK((d2.get_col(2) == std::vector<T>{7, 8, 9}));
     CHECK((MatDim(2, 3).transpose() == MatDim(3, 2)));
+    // dense_static.rs:71-96 — same layout rules for the stack-array twin
+    DenseS<T, 7, 5> ds = DenseS<T, 7, 5>::new_default();
+    CHECK((ds.get_dims() == MatDim(7, 5)));
+    DenseS<T, 3, 3> ds2 = DenseS<T, 3, 3>::from_data({{1, 2, 3}, {4, 5, 6}, {7, 8, 9}});
+    CHECK((ds2.get_col(2) == std::array<T, 3>{7, 8, 9}));
 }
 
 template <typename T> static void multiplication_tests()
@@ -80,6 +85,13 @@ template <typename T> static void multiplication_tests()
         CHECK(output_ref == output);
         // the same product through the pipelined host-to-host call, dense (column-major) result
         CHECK(m.mul_dense_into_dense(a).unwrap() == Dense<T>::from_data({{9, 7, 8, 3, 1}, {29, 35, 20, 7, 5}, {49, 63, 32, 11, 9}}));
+    }
+    {   // mul_dense_s (sparse.rs:448-466): the test_dense_mul operands as a DenseS<T,4,3>
+        DenseS<T, 4, 3> a = DenseS<T, 4, 3>::from_data({{1, 2, 3, 4}, {5, 6, 7, 8}, {9, 10, 11, 12}});
+        Csr<T> m = Csr<T>::from_data({{3, 0, 2, 0}, {7, 0, 0, 0}, {0, 2, 0, 1}, {0, 0, 1, 0}, {1, 0, 0, 0}});
+        CHECK(m.mul_dense_s(a).unwrap() == Csr<T>::from_data({{9, 29, 49}, {7, 35, 63}, {8, 20, 32}, {3, 7, 11}, {1, 5, 9}}));
+        DenseS<T, 3, 1> bad = DenseS<T, 3, 1>::new_default();
+        CHECK(m.mul_dense_s(bad).unwrap_err() == MatErr::IncorrectDimensions);
     }
     {   // test_nnz (sparse.rs:1153-1178): zero outputs are dropped by insert
         Dense<T> a = Dense<T>::from_data({{1, 0, 3, 4}, {8, 0, 0, 5}});
