@@ -307,3 +307,34 @@ def test_pipelined_host_to_host_dense_product(gpu, dtype, n):
     with pytest.raises(MatError) as e:
         a.mul_dense_into(Dense.new_default_with_dims(2, k + 1, dtype))
     assert e.value.kind == MatErr.IncorrectDimensions
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shape_sweep(gpu, seed):
+    """Randomised shapes, densities, dtypes and kernels (seeded): every draw against the oracle — bit-exact
+    for the vector kernel, bit-exact on dyadic data / within tolerance on real data for merge-path, and
+    identical results from `auto`."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(8):
+        dtype = DTYPES[int(rng.integers(0, 2))]
+        m = int(rng.choice([1, 2, 7, 33, 100, 513, 2000, 5001]))
+        k = int(rng.choice([1, 3, 64, 1000, 4099]))
+        n = int(rng.choice([1, 2, 5, 8, 16, 24, 32, 48, 64, 96, 128, 200]))
+        mean_len = float(rng.choice([0.5, 2, 7, 30, 120]))
+        giant = bool(rng.integers(0, 2)) and m > 2
+        exact = bool(rng.integers(0, 2))
+        v, ci, ri = random_csr(rng, m, k, dtype, mean_len=min(mean_len, 4.0 * k), exact=exact,
+                               giant_row=int(rng.integers(0, m)) if giant else None, giant_len=int(rng.integers(50, 3000)) if giant else 0)
+        b = random_dense(rng, k, n, dtype, exact=exact)
+        want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+        tag = f"seed={seed} {np.dtype(dtype).name} m={m} k={k} n={n} mean={mean_len} giant={giant} exact={exact}"
+        got_v, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "vector")
+        assert_bitwise(got_v, want, "vector " + tag)
+        got_m, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
+        if exact:
+            assert_bitwise(got_m, want, "merge " + tag)
+        else:
+            scale = ref_numpy.mul_dense_rowmajor(np.abs(v), ci, ri, np.abs(b))
+            assert_tolerance(got_m, want, scale, TOL[dtype], "merge " + tag)
+        got_a, info = gpu_product(gpu, (m, k), v, ci, ri, b, "auto")
+        assert_bitwise(got_a, got_v if info["algo"] == _lib.ALGO_VECTOR else got_m, "auto " + tag)
