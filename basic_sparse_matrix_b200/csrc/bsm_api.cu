@@ -622,6 +622,9 @@ static int choose_algo(const bsm_csr *a, int requested)
     // above the mean (power-law hubs, the bench-as-written matrix) needs the nnz-balanced kernel
     const double mean = a->rows ? (double)a->nnz / (double)a->rows : 0.0;
     if ((double)a->max_row_nnz > 64.0 + 8.0 * mean) return BSM_ALGO_MERGE;
+    // few, long rows (down to one giant row: a checksum vector, the bench-as-written matrix): fewer rows
+    // than the vector kernel has warps, so only an entry-balanced split fills the machine
+    if (a->rows < (uint64_t)g_rt.sm_count * 96 && a->max_row_nnz > 1024) return BSM_ALGO_MERGE;
     return BSM_ALGO_VECTOR;
 }
 
