@@ -123,6 +123,7 @@ def _declare(L):
     sig("bsm_dense_alloc", i32, i32, u64, u64, PV)
     sig("bsm_dense_borrow", i32, i32, u64, u64, vp, u64, PV)
     sig("bsm_dense_free", i32, vp)
+    sig("bsm_dense_zero", i32, vp)
     sig("bsm_dense_info", i32, vp, C.POINTER(i32), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), PV)
     sig("bsm_dense_download_rowmajor", i32, vp, vp)
     sig("bsm_dense_upload_rowmajor", i32, i32, u64, u64, vp, PV)
@@ -138,6 +139,10 @@ def _declare(L):
     sig("bsm_comm_init", i32, C.c_char_p, i32, i32, PV)
     sig("bsm_comm_free", i32, vp)
     sig("bsm_allgather_rows", i32, vp, vp, vp, vp)
+    sig("bsm_comm_barrier", i32, vp)
+    sig("bsm_spmm_scatter", i32, vp, vp, C.POINTER(vp), i32, u64, i32)
+    sig("bsm_dense_ipc_export", i32, vp, C.c_char_p)
+    sig("bsm_dense_ipc_open", i32, C.c_char_p, i32, u64, u64, u64, PV)
     sig("bsm_gen_dense", i32, i32, u64, u64, u64, i32, C.c_double, PV)
     sig("bsm_gen_laplacian", i32, i32, u64, u64, u64, u64, u64, PV)
     sig("bsm_gen_band", i32, i32, u64, u64, u64, u64, PV)

@@ -368,7 +368,16 @@ static Shape pick_shape(uint32_t n, uint64_t ldb, uint64_t ldc, uint64_t col0, c
 }
 
 // Geometry of the vector kernel for one column pass (see spmm_rows.cu).
-static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags)
+// Scatter variant of the vector kernel: C is this rank's FULL result buffer, the rank's rows start at
+// row_offset, and every row is also stored to `n_peers` further full buffers (peer GPUs over NVLink).
+struct ScatterTargets {
+    int n_peers = 0;
+    void *peer_data[7] = {};
+    uint64_t row_offset = 0;
+};
+
+static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags,
+                       const ScatterTargets *scatter = nullptr)
 {
     const size_t s = dtype_size(a->dtype);
     const uint32_t n_total = (uint32_t)b->cols;
@@ -384,7 +393,8 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
     for (uint32_t col0 = 0; col0 < n_total; col0 += tile, ++passes) {
         const uint32_t n = std::min(tile, n_total - col0);
         const char *bp = (const char *)b->data + (size_t)col0 * s;
-        char *cp = (char *)c->data + (size_t)col0 * s;
+        const size_t c_off = ((scatter ? (size_t)scatter->row_offset * c->ld : 0) + (size_t)col0) * s;
+        char *cp = (char *)c->data + c_off;
         Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows != 0);
         const uint32_t rpp = 32u / (uint32_t)sh.G;                 // rows side by side in one warp
         const uint32_t rq = std::max(4u, rpp);                     // slice granularity (rpp is a power of two)
@@ -401,6 +411,11 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         p.n = n;
         p.ldb = (uint32_t)b->ld;
         p.ldc = (uint32_t)c->ld;
+        const bool multi = scatter && scatter->n_peers > 0;
+        if (multi) {
+            p.n_peers = (uint32_t)scatter->n_peers;
+            for (int d = 0; d < scatter->n_peers; ++d) p.peers[d] = (char *)scatter->peer_data[d] + c_off;
+        }
         // rows per TMA slice: ~128 entries per bulk copy; narrow shapes (32/G rows side by side) want
         // several passes per slice to amortise the per-slice bookkeeping
         const bool user_R = tn.rows_per_slice > 0, user_nw = tn.warps_per_cta > 0;
@@ -420,6 +435,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // register tiles (measured 8 % faster at n = 128 f64), LDS.128 reads when it holds one
         int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 5) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 2) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
         if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
+        if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;       // the scatter variant exists for the default flavours
         if (flavour >= 2 && wide_full && nw > 8) nw = 8;
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
         p.flags = flags;
@@ -488,11 +504,11 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         p.num_super = (uint32_t)((a->rows + S - 1) / S);
         const int block = nw * 32;
         int occ = 0;
-        BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, flavour, block, smem, &occ));
+        BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, flavour, multi, block, smem, &occ));
         if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_vector: kernel does not fit on an SM");
         int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
         const int grid = (int)std::min<uint64_t>(p.num_super, (uint64_t)g_rt.sm_count * ctas);
-        if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, flavour, grid, block, smem, ctas, g_rt.stream));
+        if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, flavour, multi, grid, block, smem, ctas, g_rt.stream));
         g_info.kernels += grid > 0;
         g_info.vec_elems = sh.V;
         g_info.lanes_per_row = sh.G;
@@ -1129,7 +1145,17 @@ int bsm_dense_free(bsm_dense *d)
 {
     if (!d) return BSM_OK;
     if (d->owns) dev_free(d->data, d->pooled);
+    if (d->ipc && d->data) cudaIpcCloseMemHandle(d->data);
     delete d;
+    return BSM_OK;
+}
+
+int bsm_dense_zero(bsm_dense *d)
+{
+    BSM_TRY(ensure_init());
+    if (!d) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_zero: null handle");
+    const size_t bytes = (size_t)d->rows * d->ld * dtype_size(d->dtype);
+    if (bytes) BSM_CUDA(cudaMemsetAsync(d->data, 0, bytes, g_rt.stream));
     return BSM_OK;
 }
 
@@ -1190,6 +1216,65 @@ int bsm_spmm_tuned(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm
 {
     return spmm_dispatch(a, b, c, tuning);
 }
+int bsm_spmm_scatter(const bsm_csr *a, const bsm_dense *b, bsm_dense *const *c_full, int ndest, uint64_t row_offset, int algo)
+{
+    BSM_TRY(ensure_init());
+    if (!a || !b || !c_full || ndest < 1 || ndest > 8) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_scatter: bad arguments (1..8 destinations)");
+    if (a->cols != b->rows) return fail(BSM_ERR_INCORRECT_DIMENSIONS, "spmm_scatter: A.cols != B.rows (MatErr::IncorrectDimensions)");
+    ScatterTargets st;
+    st.row_offset = row_offset;
+    for (int d = 0; d < ndest; ++d) {
+        const bsm_dense *c = c_full[d];
+        if (!c) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_scatter: null destination");
+        if (c->dtype != a->dtype || b->dtype != a->dtype) return fail(BSM_ERR_DTYPE_MISMATCH, "spmm_scatter: dtype mismatch");
+        if (c->cols != b->cols || c->rows < row_offset + a->rows || c->ld != c_full[0]->ld)
+            return fail(BSM_ERR_INCORRECT_DIMENSIONS, "spmm_scatter: every destination must be (>= row_offset + A.rows) x B.cols with one leading dimension");
+        if (c->data == b->data) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_scatter: a destination aliases B");
+        if (d > 0) st.peer_data[st.n_peers++] = c->data;
+    }
+    // a row may be summed by one lane group only (its row is written, never read back): vector kernel
+    if (algo == BSM_ALGO_MERGE || (algo == BSM_ALGO_AUTO && choose_algo(a, algo) == BSM_ALGO_MERGE))
+        return fail(BSM_ERR_NOT_SUPPORTED, "spmm_scatter: the merge-path kernel revisits C rows (fix-up) and cannot scatter; "
+                                           "use bsm_spmm + bsm_allgather_rows for power-law matrices");
+    g_info = bsm_launch_info();
+    if (a->rows == 0 || b->cols == 0) return BSM_OK;
+    bsm_tuning tn{};
+    return spmm_vector(a, b, c_full[0], tn, BSM_TUNE_DEFAULT_FLAGS, &st);
+}
+
+int bsm_dense_ipc_export(const bsm_dense *d, char handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC memory handles are expected to be 64 bytes");
+    BSM_TRY(ensure_init());
+    if (!d || !handle) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_ipc_export: null argument");
+    if (!d->owns || d->pooled || d->ipc) return fail(BSM_ERR_NOT_SUPPORTED, "dense_ipc_export: only buffers from bsm_dense_alloc / upload / gen can be exported");
+    cudaIpcMemHandle_t h;
+    BSM_CUDA(cudaIpcGetMemHandle(&h, d->data));
+    memcpy(handle, &h, sizeof(h));
+    return BSM_OK;
+}
+
+int bsm_dense_ipc_open(const char handle[64], int dtype, uint64_t rows, uint64_t cols, uint64_t ld, bsm_dense **out)
+{
+    BSM_TRY(ensure_init());
+    if (!handle || !out || ld < cols) return fail(BSM_ERR_INVALID_ARGUMENT, "dense_ipc_open: bad arguments");
+    if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "dense_ipc_open: dtype must be f32 or f64");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    BSM_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    bsm_dense *d = new bsm_dense();
+    d->dtype = dtype;
+    d->rows = rows;
+    d->cols = cols;
+    d->ld = ld ? ld : 1;
+    d->data = p;
+    d->owns = false;
+    d->ipc = true;
+    *out = d;
+    return BSM_OK;
+}
+
 int bsm_last_launch_info(bsm_launch_info *info)
 {
     if (!info) return fail(BSM_ERR_INVALID_ARGUMENT, "last_launch_info: null");

@@ -81,6 +81,7 @@ struct bsm_dense {
     void *data = nullptr;
     bool owns = true;
     bool pooled = false;
+    bool ipc = false;              // mapping of another process's buffer (cudaIpcOpenMemHandle)
 };
 
 // ------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 struct bsm_comm {
     ncclComm_t comm = nullptr;
     int nranks = 0, rank = 0;
+    int *token = nullptr;   // 4 bytes of HBM for the stream-ordered barrier
 };
 
 using namespace bsm;
@@ -51,6 +52,11 @@ int bsm_comm_init(const char id[128], int nranks, int rank, bsm_comm **out)
         delete c;
         return fail(BSM_ERR_NCCL, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
     }
+    if (cudaMalloc(&c->token, 4) != cudaSuccess || cudaMemset(c->token, 0, 4) != cudaSuccess) {
+        ncclCommDestroy(c->comm);
+        delete c;
+        return fail(BSM_ERR_CUDA, "comm_init: cannot allocate the barrier token");
+    }
     *out = c;
     return BSM_OK;
 }
@@ -58,6 +64,7 @@ int bsm_comm_init(const char id[128], int nranks, int rank, bsm_comm **out)
 int bsm_comm_free(bsm_comm *c)
 {
     if (!c) return BSM_OK;
+    if (c->token) cudaFree(c->token);
     if (c->comm) ncclCommDestroy(c->comm);
     delete c;
     return BSM_OK;
@@ -87,6 +94,16 @@ int bsm_allgather_rows(bsm_comm *c, const bsm_dense *local_block, const uint64_t
         BSM_NCCL(ncclBroadcast(slot, slot, (r1 - r0) * row_bytes, ncclChar, root, c->comm, sm));
     }
     BSM_NCCL(ncclGroupEnd());
+    return BSM_OK;
+}
+
+// Stream-ordered barrier across the ranks (a 4-byte all-reduce): after it, everything every rank
+// enqueued before its own call — e.g. the P2P stores of bsm_spmm_scatter — has completed.
+int bsm_comm_barrier(bsm_comm *c)
+{
+    BSM_TRY(ensure_init());
+    if (!c) return fail(BSM_ERR_INVALID_ARGUMENT, "comm_barrier: null communicator");
+    BSM_NCCL(ncclAllReduce(c->token, c->token, 1, ncclInt, ncclSum, c->comm, rt().stream));
     return BSM_OK;
 }
 

@@ -28,11 +28,13 @@ struct RowParams {
     uint32_t cap;        // staged entries per slice (multiple of 4)
     uint32_t stages;     // TMA ring depth per warp
     uint32_t flags;      // BSM_TUNE_*
+    uint32_t n_peers;    // scatter variant: further destinations of every C row (0 = none)
+    char *peers[7];      // their C pointers, offset like C (first column of the pass, this rank's first row)
 };
 size_t row_kernel_smem_bytes(int dtype, const RowParams &p, int warps);
-// flavour: register-budget variant of the kernel (0..3, -1 = unstaged), see spmm_rows_inst.cuh
-int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int flavour, int block, size_t smem, int *blocks_per_sm);
-int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int flavour, int grid, int block, size_t smem,
+// flavour: register-budget variant of the kernel (-1 = unstaged), see spmm_rows_inst.cuh; multi: scatter variant
+int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int flavour, bool multi, int block, size_t smem, int *blocks_per_sm);
+int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int flavour, bool multi, int grid, int block, size_t smem,
                      int ctas_per_sm, cudaStream_t stream);
 
 // ---- merge-path kernel ---------------------------------------------------------------------

@@ -6,8 +6,8 @@
 
 namespace bsm {
 
-const void *row_kernel_select_f64(Shape sh, bool fulln, int flavour);
-const void *row_kernel_select_f32(Shape sh, bool fulln, int flavour);
+const void *row_kernel_select_f64(Shape sh, bool fulln, int flavour, bool multi);
+const void *row_kernel_select_f32(Shape sh, bool fulln, int flavour, bool multi);
 
 size_t row_kernel_smem_bytes(int dtype, const RowParams &p, int warps)
 {
@@ -15,15 +15,15 @@ size_t row_kernel_smem_bytes(int dtype, const RowParams &p, int warps)
     return ring + (size_t)warps * p.stages * 8;   // + one mbarrier per (warp, stage)
 }
 
-static const void *row_kernel_select(int dtype, Shape sh, uint32_t n, int flavour)
+static const void *row_kernel_select(int dtype, Shape sh, uint32_t n, int flavour, bool multi)
 {
     const bool fulln = n == (uint32_t)(sh.V * sh.G * sh.NT);
-    return dtype == BSM_F64 ? row_kernel_select_f64(sh, fulln, flavour) : row_kernel_select_f32(sh, fulln, flavour);
+    return dtype == BSM_F64 ? row_kernel_select_f64(sh, fulln, flavour, multi) : row_kernel_select_f32(sh, fulln, flavour, multi);
 }
 
-int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int flavour, int block, size_t smem, int *blocks_per_sm)
+int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int flavour, bool multi, int block, size_t smem, int *blocks_per_sm)
 {
-    const void *k = row_kernel_select(dtype, sh, n, flavour);
+    const void *k = row_kernel_select(dtype, sh, n, flavour, multi);
     if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rows: no kernel for this lane shape");
     BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // query under the largest carve-out (launch_spmm_rows narrows it to what the chosen residency needs)
@@ -32,10 +32,10 @@ int row_kernel_occupancy(int dtype, Shape sh, uint32_t n, int flavour, int block
     return BSM_OK;
 }
 
-int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int flavour, int grid, int block, size_t smem, int ctas_per_sm,
+int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int flavour, bool multi, int grid, int block, size_t smem, int ctas_per_sm,
                      cudaStream_t stream)
 {
-    const void *k = row_kernel_select(dtype, sh, p.n, flavour);
+    const void *k = row_kernel_select(dtype, sh, p.n, flavour, multi);
     if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rows: no kernel for this lane shape");
     if (p.stages < 1 || p.stages > (uint32_t)kMaxStages) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_rows: stages out of range");
     if (p.R == 0 || p.R % 4 || p.P % p.R)

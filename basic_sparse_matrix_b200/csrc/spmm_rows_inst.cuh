@@ -7,10 +7,10 @@ namespace bsm {
 
 constexpr int row_default_u(int NT) { return NT >= 4 ? 2 : (NT == 2 ? 4 : 8); }
 
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true, bool MULTI = false>
 static const void *rk()
 {
-    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA>);
+    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI>);
 }
 
 // Register-budget flavours (`flavour` argument of the selectors):
@@ -21,9 +21,15 @@ static const void *rk()
 //   4: flavour 2 with scalar (one LDS per entry) instead of LDS.128 reads of col_idx / values
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
 // G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
-template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int flavour)
+// `multi` (scatter of C rows to peer GPUs) exists for the default flavour of every shape and for the unstaged one.
+template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int flavour, bool multi)
 {
     constexpr int U1 = row_default_u(NT), U2 = 2 * U1;
+    if (multi) {
+        if (flavour < 0) return fulln ? rk<T, V, 32, NT, true, U1, 512, 1, false, true, true>() : rk<T, V, 32, NT, false, U1, 512, 1, false, true, true>();
+        if (!fulln) return rk<T, V, 32, NT, false, U1, 512, 1, true, true, true>();
+        return flavour == 4 ? rk<T, V, 32, NT, true, U1, 256, 3, true, false, true>() : rk<T, V, 32, NT, true, U1, 256, 3, true, true, true>();
+    }
     if (flavour < 0) return fulln ? rk<T, V, 32, NT, true, U1, 512, 1, false>() : rk<T, V, 32, NT, false, U1, 512, 1, false>();
     if (fulln) {
         switch (flavour) {
@@ -37,30 +43,34 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
     return rk<T, V, 32, NT, false, U1, 512, 1>();
 }
 
-template <typename T, int V, int G> static const void *rk_narrow(bool fulln, int flavour)
+template <typename T, int V, int G> static const void *rk_narrow(bool fulln, int flavour, bool multi)
 {
+    if (multi) {
+        if (flavour < 0) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, false, true, true>() : rk<T, V, G, 1, false, 8, 512, 1, false, true, true>();
+        return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, true, true>() : rk<T, V, G, 1, false, 8, 512, 1, true, true, true>();
+    }
     if (flavour < 0) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, false>() : rk<T, V, G, 1, false, 8, 512, 1, false>();
     if (flavour == 4) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, false>() : rk<T, V, G, 1, false, 8, 512, 1, true, false>();   // scalar A reads
     return fulln ? rk<T, V, G, 1, true, 8, 512, 1>() : rk<T, V, G, 1, false, 8, 512, 1>();
 }
 
-template <typename T, int V> static const void *row_kernel_select_v(Shape sh, bool fulln, int flavour)
+template <typename T, int V> static const void *row_kernel_select_v(Shape sh, bool fulln, int flavour, bool multi)
 {
     if (sh.G == 32) {
         switch (sh.NT) {
-            case 1: return rk_wide<T, V, 1>(fulln, flavour);
-            case 2: return rk_wide<T, V, 2>(fulln, flavour);
-            case 4: return rk_wide<T, V, 4>(fulln, flavour);
+            case 1: return rk_wide<T, V, 1>(fulln, flavour, multi);
+            case 2: return rk_wide<T, V, 2>(fulln, flavour, multi);
+            case 4: return rk_wide<T, V, 4>(fulln, flavour, multi);
         }
         return nullptr;
     }
     if (sh.NT != 1) return nullptr;
     switch (sh.G) {
-        case 16: return rk_narrow<T, V, 16>(fulln, flavour);
-        case 8: return rk_narrow<T, V, 8>(fulln, flavour);
-        case 4: return rk_narrow<T, V, 4>(fulln, flavour);
-        case 2: return rk_narrow<T, V, 2>(fulln, flavour);
-        case 1: return rk_narrow<T, V, 1>(fulln, flavour);
+        case 16: return rk_narrow<T, V, 16>(fulln, flavour, multi);
+        case 8: return rk_narrow<T, V, 8>(fulln, flavour, multi);
+        case 4: return rk_narrow<T, V, 4>(fulln, flavour, multi);
+        case 2: return rk_narrow<T, V, 2>(fulln, flavour, multi);
+        case 1: return rk_narrow<T, V, 1>(fulln, flavour, multi);
     }
     return nullptr;
 }

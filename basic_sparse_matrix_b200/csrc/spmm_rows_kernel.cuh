@@ -50,11 +50,14 @@ __host__ __device__ inline RowSmemLayout row_layout(uint32_t cap, uint32_t R, ui
 // (shared memory when the slice was staged by TMA, else the global arrays with base = 0).
 // VECA: col_idx / values sit in a 16-byte aligned shared-memory stage (padded past the slice), so the A
 // stream is read four columns / two or four values per LDS.128 instead of one scalar LDS per entry.
-template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA>
+// MULTI: every C row is also written to p.n_peers further destinations (the full result buffers of the
+// other GPUs, mapped over NVLink): multiply and all-gather in one kernel, P2P stores instead of a
+// collective. `lane_off` = byte offset of the lane's first column inside a row.
+template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA, bool MULTI>
 __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t *__restrict__ rp, const uint32_t *__restrict__ ci,
                                               const T *__restrict__ va, uint32_t base, uint32_t row0, uint32_t nr,
                                               const char *__restrict__ b_bytes, char *__restrict__ c_bytes, const bool (&col_ok)[NT],
-                                              uint32_t grp, bool streaming)
+                                              uint32_t grp, bool streaming, uint32_t lane_off)
 {
     constexpr int RPP = 32 / G;
     const uint32_t ldb_bytes = p.ldb * (uint32_t)sizeof(T);
@@ -69,11 +72,16 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
         for (int t = 0; t < NT; ++t) acc[t].zero();                   // T::default()  sparse.rs:434
         uint32_t rr = 0;                                               // row being accumulated (slice-local)
         uint32_t row_end = rp[1];
-        char *crow = c_bytes + (size_t)row0 * ldc_bytes;
+        size_t crow = (size_t)row0 * ldc_bytes;   // byte offset of the row inside C (and inside every peer copy)
         auto close_row = [&]() {
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                if (FULLN || col_ok[t]) acc[t].store(reinterpret_cast<T *>(crow) + t * G * V, streaming);
+                if (FULLN || col_ok[t]) {
+                    acc[t].store(reinterpret_cast<T *>(c_bytes + crow) + t * G * V, streaming);
+                    if constexpr (MULTI)
+                        for (uint32_t d = 0; d < p.n_peers; ++d)
+                            acc[t].store(reinterpret_cast<T *>(p.peers[d] + lane_off + crow) + t * G * V, false);
+                }
                 acc[t].zero();
             }
             crow += ldc_bytes;
@@ -92,10 +100,15 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
 #pragma unroll
             for (int t = 0; t < NT; ++t) acc[t].zero();
             stream_entries<T, V, NT, FULLN, U, VECA, false>(ci, va, s, e, b_bytes, ldb_bytes, col_ok, G, acc, [](uint32_t) {});
-            T *crow = reinterpret_cast<T *>(c_bytes + (size_t)(row0 + r) * ldc_bytes);
+            const size_t crow = (size_t)(row0 + r) * ldc_bytes;
 #pragma unroll
             for (int t = 0; t < NT; ++t)
-                if (FULLN || col_ok[t]) acc[t].store(crow + t * G * V, streaming);
+                if (FULLN || col_ok[t]) {
+                    acc[t].store(reinterpret_cast<T *>(c_bytes + crow) + t * G * V, streaming);
+                    if constexpr (MULTI)
+                        for (uint32_t d = 0; d < p.n_peers; ++d)
+                            acc[t].store(reinterpret_cast<T *>(p.peers[d] + lane_off + crow) + t * G * V, false);
+                }
         }
     }
 }
@@ -104,7 +117,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
 // as entry k has been consumed); MAXT / MINB = launch bounds (threads per CTA, CTAs per SM the register allocation must allow).
 // STAGED = col_idx / values of every slice fit the TMA stage (the host guarantees it from the longest
 // row); the unstaged variant reads them from global memory and stages only the row_ptr windows.
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED, bool VECA = true>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED, bool VECA = true, bool MULTI = false>
 __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -197,11 +210,12 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
             const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
             const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
             if constexpr (STAGED)
-                process_slice<T, V, G, NT, FULLN, U, VECA>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
-                                                     reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes, c_bytes,
-                                                     col_ok, grp, streaming);
+                process_slice<T, V, G, NT, FULLN, U, VECA, MULTI>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
+                                                            reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,
+                                                            c_bytes, col_ok, grp, streaming, gl * V * (uint32_t)sizeof(T));
             else
-                process_slice<T, V, G, NT, FULLN, U, false>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, streaming);
+                process_slice<T, V, G, NT, FULLN, U, false, MULTI>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp,
+                                                                   streaming, gl * V * (uint32_t)sizeof(T));
         }
     }
 }

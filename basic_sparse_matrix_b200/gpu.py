@@ -41,6 +41,11 @@ def l2_flush() -> None:
     check(lib().bsm_l2_flush())
 
 
+def fill_zero(d: "DeviceDense") -> None:
+    """Zero a device-resident dense matrix on the library stream."""
+    check(lib().bsm_dense_zero(d.handle))
+
+
 def kernel_launch_count() -> int:
     return int(lib().bsm_kernel_launch_count())
 
@@ -163,6 +168,18 @@ class DeviceDense(_Handle):
         check(lib().bsm_dense_residual_norm(self.handle, b.handle, C.byref(r), C.byref(n)))
         return r.value, n.value
 
+    def ipc_export(self) -> bytes:
+        """64 opaque bytes another process of the same box can open with ``DeviceDense.ipc_open``."""
+        buf = C.create_string_buffer(64)
+        check(lib().bsm_dense_ipc_export(self.handle, buf))
+        return buf.raw
+
+    @classmethod
+    def ipc_open(cls, handle: bytes, rows: int, cols: int, ld: int, dtype) -> "DeviceDense":
+        out = C.c_void_p()
+        check(lib().bsm_dense_ipc_open(handle, _lib.dtype_code(dtype), rows, cols, ld, C.byref(out)))
+        return cls(out.value)
+
     def into_csr(self) -> "DeviceCsr":
         """Zero-dropping compaction = the reference's result construction (sparse.rs:442, 222-233,
         206-219), on the device."""
@@ -246,6 +263,15 @@ class DeviceCsr(_Handle):
         return out
 
 
+    def mul_dense_scatter(self, rhs: DeviceDense, full_buffers, row_offset: int, algo="auto") -> None:
+        """Fused multiply + all-gather: every finished C row goes to ``full_buffers[0]`` (this rank's full
+        result) and to all the others (peer GPUs' full results, mapped with ``ipc_open``), at global row
+        ``row_offset + local row``. No collective; barrier across ranks before reading."""
+        arr = (C.c_void_p * len(full_buffers))(*[f.handle for f in full_buffers])
+        check(lib().bsm_spmm_scatter(self.handle, rhs.handle, arr, len(full_buffers), row_offset,
+                                     _lib.ALGO_NAMES[algo] if isinstance(algo, str) else algo))
+
+
 # ---- row-partitioned multi-GPU ------------------------------------------------------------------
 def partition_rows(row_index: np.ndarray, parts: int) -> np.ndarray:
     """nnz-balanced contiguous row split (host): ``bounds[p]`` = first row of part ``p``."""
@@ -270,6 +296,9 @@ class Comm(_Handle):
         out = C.c_void_p()
         check(lib().bsm_comm_init(unique_id, nranks, rank, C.byref(out)))
         return cls(out.value)
+
+    def barrier(self) -> None:
+        check(lib().bsm_comm_barrier(self.handle))
 
     def allgather_rows(self, local_block: DeviceDense, bounds: np.ndarray, full: DeviceDense) -> None:
         b = np.ascontiguousarray(bounds, dtype=np.uint64)

@@ -169,6 +169,18 @@ def k_ref_of(kind, prm, rows_total, r0, r1):
     return min(rows_total, r1 + reach) - max(0, r0 - reach)
 
 
+def sample_dense_rows(gpu, dense, row_ids):
+    """Download selected rows of a device-resident dense matrix (one-row borrowed views)."""
+    i = dense.info()
+    sz = np.dtype(i["dtype"]).itemsize
+    out = np.empty((len(row_ids), i["cols"]), i["dtype"])
+    for j, r in enumerate(row_ids):
+        view = gpu.DeviceDense.borrow(i["ptr"] + int(r) * i["ld"] * sz, 1, i["cols"], i["ld"], i["dtype"])
+        out[j] = view.to_rowmajor()[0]
+        view.close()
+    return out
+
+
 def time_device_steps(torch, A, B, C, steps, warmup, tuning=None, barrier=None):
     """W untimed + K timed launches on torch's current stream; per-launch CUDA events."""
     for _ in range(warmup):
@@ -460,6 +472,45 @@ def main():
         g_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
         gather = {"allgather_ms": round(float(g_ms.item()), 3), "bytes_received_per_gpu": int((rows_total - ai["rows"]) * n * s)}
+        # the same gathered product WITHOUT the collective: the SpMM kernel stores every C row into every
+        # rank's full buffer (peer memory over NVLink, mapped with CUDA IPC): multiply + gather in one kernel
+        try:
+            ids = np.unique(np.concatenate([np.linspace(0, rows_total - 1, 96).astype(np.int64), bounds[:-1], bounds[1:] - 1]))
+            ref_rows = sample_dense_rows(gpu, full, ids)          # from the NCCL all-gather above
+            fi = full.info()
+            handles = [None] * world
+            dist.all_gather_object(handles, full.ipc_export())
+            peers = [gpu.DeviceDense.ipc_open(handles[r], rows_total, n, fi["ld"], dtype) for r in range(world) if r != rank]
+            dests = [full] + peers
+            torch.cuda.synchronize()
+            dist.barrier()
+            gpu.fill_zero(full)                                    # so that the check below sees only what the fused kernel wrote
+            torch.cuda.synchronize()
+            dist.barrier()
+            A.mul_dense_scatter(B, dests, r0)                      # warm-up (maps peer pages)
+            comm.barrier()
+            torch.cuda.synchronize()
+            dist.barrier()
+            reps = 3
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(reps):
+                A.mul_dense_scatter(B, dests, r0)
+                comm.barrier()
+            f1.record()
+            torch.cuda.synchronize()
+            f_ms = torch.tensor([f0.elapsed_time(f1) / reps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(f_ms, op=dist.ReduceOp.MAX)
+            same = bool(np.array_equal(sample_dense_rows(gpu, full, ids).view(np.uint8), ref_rows.view(np.uint8)))
+            gather.update({"fused_scatter_ms": round(float(f_ms.item()), 3),
+                           "spmm_plus_allgather_ms": round(total_ms_max / args.steps + float(g_ms.item()), 3),
+                           "fused_matches_allgather_on_sampled_rows": same,
+                           "fused_path": "bsm_spmm_scatter: P2P stores of every C row to all ranks' full buffers (CUDA IPC), then a 4-byte NCCL barrier"})
+            dist.barrier()
+            for h in peers:
+                h.close()
+        except Exception as ex:
+            gather["fused_scatter_error"] = str(ex)[:300]
         full.close()
         comm.close()
 

@@ -158,6 +158,7 @@ int bsm_dense_alloc(int dtype, uint64_t rows, uint64_t cols, bsm_dense **out);
 int bsm_dense_borrow(int dtype, uint64_t rows, uint64_t cols, void *d_rowmajor, uint64_t ld,
                      bsm_dense **out);
 int bsm_dense_free(bsm_dense *d);
+int bsm_dense_zero(bsm_dense *d);   /* all elements (padding columns included) = 0, on the library stream */
 int bsm_dense_info(const bsm_dense *d, int *dtype, uint64_t *rows, uint64_t *cols, uint64_t *ld,
                    void **d_ptr);
 /* Download into host columns (col_ptrs[c] has room for `rows` elements). */
@@ -246,6 +247,21 @@ int bsm_comm_free(bsm_comm *c);
 /* full (rows_total x cols, row-major, on every rank) <- concat over ranks of local blocks;
  * bounds[] as returned by bsm_partition_rows (nranks+1 entries). */
 int bsm_allgather_rows(bsm_comm *c, const bsm_dense *local_block, const uint64_t *bounds, bsm_dense *full);
+
+/* Gathered product WITHOUT a collective: C_full[0] is this rank's full (rows_total x n) result buffer,
+ * C_full[1..ndest-1] are the other ranks' full buffers mapped into this process (bsm_dense_ipc_open).
+ * The SpMM kernel stores every row it finishes (global row = row_offset + local row) to ALL of them —
+ * multiply and all-gather fused into one kernel, P2P stores over NVLink instead of NCCL. Follow with
+ * bsm_comm_barrier (or any cross-rank barrier) before reading a full buffer. Vector-CSR kernel only:
+ * the merge-path kernel revisits C rows and returns BSM_ERR_NOT_SUPPORTED here. */
+int bsm_spmm_scatter(const bsm_csr *a, const bsm_dense *b, bsm_dense *const *c_full, int ndest,
+                     uint64_t row_offset, int algo);
+/* CUDA IPC plumbing for the above: export a library-allocated dense buffer as 64 opaque bytes, ship
+ * them to the other processes of the box, open them there (free with bsm_dense_free). */
+int bsm_dense_ipc_export(const bsm_dense *d, char handle[64]);
+int bsm_dense_ipc_open(const char handle[64], int dtype, uint64_t rows, uint64_t cols, uint64_t ld,
+                       bsm_dense **out);
+int bsm_comm_barrier(bsm_comm *c);
 
 /* ------------------------------------------------------------------------------------------
  * Synthetic workloads generated directly in HBM (bench / test support; counter-based hash so

@@ -69,6 +69,12 @@ extern "C" {
     pub fn bsm_comm_unique_id(id: *mut c_char) -> c_int;
     pub fn bsm_comm_init(id: *const c_char, nranks: c_int, rank: c_int, out: *mut *mut bsm_comm) -> c_int;
     pub fn bsm_comm_free(c: *mut bsm_comm) -> c_int;
+    /// multiply + all-gather fused: every C row is stored to all destinations (own + peer GPUs, P2P over NVLink)
+    pub fn bsm_spmm_scatter(a: *const bsm_csr, b: *const bsm_dense, c_full: *const *mut bsm_dense, ndest: c_int,
+                            row_offset: u64, algo: c_int) -> c_int;
+    pub fn bsm_dense_ipc_export(d: *const bsm_dense, handle: *mut c_char) -> c_int;
+    pub fn bsm_dense_ipc_open(handle: *const c_char, dtype: c_int, rows: u64, cols: u64, ld: u64, out: *mut *mut bsm_dense) -> c_int;
+    pub fn bsm_comm_barrier(c: *mut bsm_comm) -> c_int;
     pub fn bsm_allgather_rows(c: *mut bsm_comm, local_block: *const bsm_dense, bounds: *const u64,
                               full: *mut bsm_dense) -> c_int;
 }

@@ -338,3 +338,34 @@ def test_random_shape_sweep(gpu, seed):
             assert_tolerance(got_m, want, scale, TOL[dtype], "merge " + tag)
         got_a, info = gpu_product(gpu, (m, k), v, ci, ri, b, "auto")
         assert_bitwise(got_a, got_v if info["algo"] == _lib.ALGO_VECTOR else got_m, "auto " + tag)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 10, 32, 64, 128, 200])
+def test_scatter_variant_writes_every_destination(gpu, dtype, n):
+    """bsm_spmm_scatter (multiply + all-gather fused, P2P stores): on one GPU the "peers" are three local
+    full-size buffers; each must receive this rank's rows at row_offset, bit-identical to the plain
+    product, and nothing else."""
+    rng = np.random.default_rng(33)
+    m, k, off, total = 700, 900, 123, 1000
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=6)
+    b = random_dense(rng, k, n, dtype)
+    want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+    a = gpu.DeviceCsr.from_host(host_csr((m, k), v, ci, ri))
+    bd = gpu.DeviceDense.from_rowmajor(b)
+    sentinel = np.full((total, n), 7.25, dtype)
+    fulls = [gpu.DeviceDense.from_rowmajor(sentinel) for _ in range(3)]
+    a.mul_dense_scatter(bd, fulls, off, algo="vector")
+    for f in fulls:
+        got = f.to_rowmajor()
+        assert_bitwise(got[off:off + m], want, f"scatter n={n}")
+        assert np.all(got[:off] == 7.25) and np.all(got[off + m:] == 7.25)
+    # dimension and kernel-family errors
+    with pytest.raises(MatError) as e:
+        a.mul_dense_scatter(bd, fulls, total - m + 1)
+    assert e.value.kind == MatErr.IncorrectDimensions
+    with pytest.raises(_lib.BsmError) as e2:
+        a.mul_dense_scatter(bd, fulls, off, algo="merge")
+    assert e2.value.status == _lib.BSM_ERR_NOT_SUPPORTED
+    for h in fulls + [a, bd]:
+        h.close()
