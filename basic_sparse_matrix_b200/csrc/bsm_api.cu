@@ -435,6 +435,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // register tiles (measured 8 % faster at n = 128 f64), LDS.128 reads when it holds one
         int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 5) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 2) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
         if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
+        if (flavour == 3) flavour = 2;   // retired flavour
         if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;       // the scatter variant exists for the default flavours
         if (flavour >= 2 && wide_full && nw > 8) nw = 8;
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
@@ -445,7 +446,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // hardware limit. If even the smallest slice cannot be staged, col_idx / values are read from
         // global memory instead (unstaged variant).
         const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
-        const int resident = (flavour == 2 || (flavour == 4 && wide_full)) ? 3 : (flavour == 3 ? 4 : 1);
+        const int resident = (flavour == 2 || (flavour == 4 && wide_full)) ? 3 : 1;
         const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (160 * 1024) / resident);
         const uint32_t window = (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight (U)
         p.R = R;

@@ -17,7 +17,7 @@ static const void *rk()
 //   0: CTAs of up to 512 threads, 1 per SM (<= 128 registers)       — the default
 //   1: same, gather window twice as deep
 //   2: CTAs of up to 256 threads, 3 per SM (<= 85 registers)
-//   3: CTAs of up to 256 threads, 4 per SM (<= 64 registers)
+//   3: (retired: 4 CTAs of 256 threads at <= 64 registers spilled and measured slower; runs as 2)
 //   4: flavour 2 with scalar (one LDS per entry) instead of LDS.128 reads of col_idx / values
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
 // G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
@@ -35,7 +35,6 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
         switch (flavour) {
             case 1: return rk<T, V, 32, NT, true, U2, 512, 1>();
             case 2: return rk<T, V, 32, NT, true, U1, 256, 3>();
-            case 3: return rk<T, V, 32, NT, true, U1, 256, 4>();
             case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // flavour 2 with scalar A-stream reads
         }
         return rk<T, V, 32, NT, true, U1, 512, 1>();

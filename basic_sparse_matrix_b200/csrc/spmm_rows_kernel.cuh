@@ -141,18 +141,27 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
     const uint32_t my_supers = blockIdx.x < p.num_super ? (p.num_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     const uint32_t my_slices = my_supers * spw;
 
-    // first row of this warp's i-th slice
-    auto slice_row0 = [&](uint32_t i) -> uint64_t {
+    // Slice bookkeeping. Narrow shapes (G < 32) have short slices (a few row passes) and registers to
+    // spare: incremental cursors, no divisions in the loop. Wide shapes have long slices and a tight
+    // register budget: the slice position is recomputed from the slice index.
+    constexpr bool kCursor = G < 32;
+    const uint64_t sb_step = (uint64_t)gridDim.x * S;
+    const uint64_t warp_row = (uint64_t)blockIdx.x * S + (uint64_t)warp * p.P;
+    auto slice_row0 = [&](uint32_t i) -> uint64_t {   // first row of this warp's i-th slice
         const uint32_t k = i / spw, t = i - k * spw;
-        return (uint64_t)(blockIdx.x + k * gridDim.x) * S + (uint64_t)warp * p.P + (uint64_t)t * p.R;
+        return warp_row + (uint64_t)k * sb_step + (uint64_t)t * p.R;
     };
 
-    // ---- producer side (lane 0): TMA bulk copies of one slice into ring stage i % stages --------
+    // ---- producer side (lane 0): TMA bulk copies of one slice into its ring stage -----------------
     const uint64_t policy = (p.flags & BSM_TUNE_A_EVICT_FIRST) ? l2_policy_evict_first() : l2_policy_evict_normal();
-    uint32_t pf_s = 0, pf_e = 0;                // entry range of the next slice to issue (prefetched)
-    auto prefetch_bounds = [&](uint32_t i) {
-        if (i < my_slices) {
-            const uint64_t r0 = slice_row0(i);
+    uint64_t p_base = warp_row;                 // cursor of the next slice to issue (kCursor)
+    uint32_t p_t = 0, p_stage = 0;
+    uint32_t p_next = 0;                        // index of the next slice to issue
+    uint32_t pf_s = 0, pf_e = 0;                // its entry range (prefetched)
+    auto next_row0 = [&]() -> uint64_t { return kCursor ? p_base + (uint64_t)p_t * p.R : slice_row0(p_next); };
+    auto prefetch_bounds = [&]() {
+        if (p_next < my_slices) {
+            const uint64_t r0 = next_row0();
             if (r0 < p.rows) {
                 const uint32_t r1 = (uint32_t)min(r0 + p.R, (uint64_t)p.rows);
                 pf_s = __ldg(p.row_ptr + r0);
@@ -160,12 +169,12 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
             }
         }
     };
-    auto issue = [&](uint32_t i) {
-        // only lane 0 calls this
-        const uint64_t r0 = slice_row0(i);
+    auto issue = [&]() {
+        // only lane 0 calls this, with p_next < my_slices
+        const uint64_t r0 = next_row0();
+        const uint32_t stage = kCursor ? p_stage : p_next % p.stages;
         if (r0 < p.rows) {
             const uint32_t nr = (uint32_t)min((uint64_t)p.R, p.rows - r0);
-            const uint32_t stage = i % p.stages;
             unsigned char *st = ring + (size_t)stage * L.stage_bytes;
             const uint32_t base = pf_s & ~3u;                     // 16-byte aligned start for u32 and T
             const uint32_t cnt = STAGED ? ((pf_e - base + 3u) & ~3u) : 0u;   // entries, multiple of 4
@@ -178,12 +187,20 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
                 bulk_g2s(st + L.vals_off, vals + base, cnt * (uint32_t)sizeof(T), &full_bar[stage], policy);
             }
         }
-        prefetch_bounds(i + 1);
+        ++p_next;
+        if constexpr (kCursor) {
+            if (++p_t == spw) {
+                p_t = 0;
+                p_base += sb_step;
+            }
+            if (++p_stage == p.stages) p_stage = 0;
+        }
+        prefetch_bounds();
     };
 
     if (lane == 0) {
-        prefetch_bounds(0);
-        for (uint32_t i = 0; i + 1 < p.stages && i < my_slices; ++i) issue(i);
+        prefetch_bounds();
+        for (uint32_t i = 0; i + 1 < p.stages && p_next < my_slices; ++i) issue();
     }
 
     // ---- consumer side -------------------------------------------------------------------------
@@ -196,16 +213,35 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
     char *__restrict__ c_bytes = reinterpret_cast<char *>(static_cast<T *>(p.C) + gl * V);
     const bool streaming = (p.flags & BSM_TUNE_C_STREAMING) != 0;
 
+    uint64_t c_base = warp_row;                 // consumer cursor (kCursor)
+    uint32_t c_t = 0, c_stage = 0, c_phase = 0;
     for (uint32_t i = 0; i < my_slices; ++i) {
         __syncwarp();   // every lane is done reading the stage that is refilled next
-        if (lane == 0 && i + p.stages - 1 < my_slices) issue(i + p.stages - 1);
+        if (lane == 0 && p_next < my_slices) issue();
 
-        const uint64_t row0_64 = slice_row0(i);
+        uint64_t row0_64;
+        uint32_t stage, phase;
+        if constexpr (kCursor) {
+            row0_64 = c_base + (uint64_t)c_t * p.R;
+            stage = c_stage;
+            phase = c_phase;
+            if (++c_t == spw) {
+                c_t = 0;
+                c_base += sb_step;
+            }
+            if (++c_stage == p.stages) {
+                c_stage = 0;
+                c_phase ^= 1u;
+            }
+        } else {
+            row0_64 = slice_row0(i);
+            stage = i % p.stages;
+            phase = (i / p.stages) & 1u;
+        }
         if (row0_64 < p.rows) {
             const uint32_t row0 = (uint32_t)row0_64;
             const uint32_t nr = min(p.R, p.rows - row0);
-            const uint32_t stage = i % p.stages;
-            mbar_wait(&full_bar[stage], (i / p.stages) & 1u);   // TMA bytes of this slice have landed
+            mbar_wait(&full_bar[stage], phase);   // TMA bytes of this slice have landed
 
             const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
             const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);

@@ -79,7 +79,7 @@ typedef struct bsm_tuning {
     int32_t prefer_wide_rows;/* 1: full warp per row even when 128-bit loads need fewer lanes       */
     int32_t reg_flavour;     /* vector kernel: register-budget variant. 0 = heuristic; 1 = CTAs of <= 512
                                 threads, 1 per SM; 2 = same with a gather window twice as deep;
-                                3 = CTAs of <= 256 threads, 3 per SM; 4 = <= 256 threads, 4 per SM;
+                                3 = CTAs of <= 256 threads, 3 per SM; 4 = retired (runs as 3);
                                 5 = 3 with scalar instead of LDS.128 reads of col_idx / values
                                 (see csrc/spmm_rows_inst.cuh)                                        */
     int32_t reserved[5];
