@@ -14,7 +14,8 @@ import numpy as np
 from .util import MatErr, MatError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbsm_b200.so")
+# BSM_B200_LIB points at another build of the same library (A/B timing of two builds on one box)
+LIB_PATH = os.environ.get("BSM_B200_LIB") or os.path.join(_HERE, "lib", "libbsm_b200.so")
 
 BSM_OK = 0
 BSM_ERR_INCORRECT_DIMENSIONS = 1

@@ -37,9 +37,9 @@ __device__ __forceinline__ void fma_row(Lane<T, V> (&acc)[NT], const Lane<T, V> 
 //   entries and which is padded >= 2U+4 entries past e; the A stream is then read four columns and
 //   16 bytes of values per LDS.128 instead of two scalar LDS per entry. Chunks start at multiples of
 //   4; the up to three entries before s are skipped like the tail.
-// (The LDS.128 prologue fills every slot unconditionally — out-of-range slots re-read the first entry's
-// B row; the scalar prologue is predicated, so short rows issue no redundant gathers.)
-template <typename T, int V, int NT, bool FULLN, int U, bool VECA, bool FUSED, typename OnEntry>
+//   SHORT: the stream is often shorter than the window (one short row per lane group): the prologue is
+//   predicated instead of filling every slot.
+template <typename T, int V, int NT, bool FULLN, int U, bool VECA, bool FUSED, bool SHORT, typename OnEntry>
 __device__ __forceinline__ void stream_entries(const uint32_t *__restrict__ ci, const T *__restrict__ va, uint32_t s, uint32_t e,
                                                const char *__restrict__ b_bytes, uint32_t ldb_bytes, const bool (&col_ok)[NT], int G,
                                                Lane<T, V> (&acc)[NT], OnEntry &&on_entry)
@@ -89,8 +89,13 @@ __device__ __forceinline__ void stream_entries(const uint32_t *__restrict__ ci, 
         for (; kk < e; kk += U) chunk(kk, std::true_type{});             // drain
     } else {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (s + u < e) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[s + u], col_ok, G);
+        for (int u = 0; u < U; ++u) {
+            if constexpr (SHORT) {   // streams often shorter than the window (SpMV rows): no redundant gathers
+                if (s + u < e) load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[s + u], col_ok, G);
+            } else {                 // long streams: fill every slot unconditionally (past the end: the last entry again)
+                load_brow<T, V, NT, FULLN>(b[u], b_bytes, ldb_bytes, ci[min(s + u, e - 1u)], col_ok, G);
+            }
+        }
         uint32_t k = s;
         for (; k + 2 * U <= e; k += U) {   // steady state: no bounds checks
 #pragma unroll
