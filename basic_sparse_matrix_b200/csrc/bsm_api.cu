@@ -398,7 +398,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows != 0);
         const uint32_t rpp = 32u / (uint32_t)sh.G;                 // rows side by side in one warp
         const uint32_t rq = std::max(4u, rpp);                     // slice granularity (rpp is a power of two)
-        int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 16) : 16;
+        int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 24) : 16;
         // small matrices: do not leave SMs idle behind a handful of fat super-batches
         while (tn.warps_per_cta <= 0 && nw > 2 && (uint64_t)nw * rq * (uint64_t)g_rt.sm_count > a->rows) nw /= 2;
         RowParams p{};
@@ -431,13 +431,17 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         R = std::max(rq, R / rq * rq);
         // register-budget flavour (spmm_rows_inst.cuh); flavours 2 and 3 exist for full-width G == 32 shapes
         const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
-        // default for full-width shapes: 3 CTAs x 8 warps per SM; scalar A-stream reads when a lane holds several
-        // register tiles (measured 8 % faster at n = 128 f64), LDS.128 reads when it holds one
-        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 5) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 2) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
+        // defaults for full-width shapes, from the same-box A/B sweeps in profiles/: several register tiles per
+        // lane -> 3 CTAs x 8 warps per SM; one tile per lane -> one CTA of 24 warps (24 adjacent lines share
+        // L1); scalar A-stream reads in both (LDS.128 reads measured 5-8 % slower)
+        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 7) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 6) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
         if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
         if (flavour == 3) flavour = 2;   // retired flavour
         if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;       // the scatter variant exists for the default flavours
-        if (flavour >= 2 && wide_full && nw > 8) nw = 8;
+        // threads per CTA each flavour was compiled for (spmm_rows_inst.cuh)
+        const int max_warps = (flavour >= 5 && wide_full) ? 24 : ((flavour >= 2 && wide_full) ? 8 : 16);
+        if (flavour >= 5 && wide_full && !user_nw) nw = 24;
+        nw = std::min(nw, max_warps);
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
         p.flags = flags;
         // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start).
@@ -446,7 +450,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // hardware limit. If even the smallest slice cannot be staged, col_idx / values are read from
         // global memory instead (unstaged variant).
         const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
-        const int resident = (flavour == 2 || (flavour == 4 && wide_full)) ? 3 : 1;
+        const int resident = (flavour == 2 || (flavour == 4 && wide_full)) ? 3 : 1;   // CTAs per SM the flavour targets
         const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (160 * 1024) / resident);
         const uint32_t window = (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight (U)
         p.R = R;

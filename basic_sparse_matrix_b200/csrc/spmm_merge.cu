@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
     };
 
     // stored order inside the chunk, FMA; rows (possibly empty) that end before an entry are closed first
-    stream_entries<T, V, NT, FULLN, U, true, true, false>(idx_s - z_a, val_s - z_a, nz, nz_end, b_bytes, ldb_bytes, col_ok, G, acc,
+#ifdef BSM_MERGE_SCALAR_A
+    constexpr bool kVecA = false;
+#else
+    constexpr bool kVecA = true;
+#endif
+    stream_entries<T, V, NT, FULLN, U, kVecA, true, false>(idx_s - z_a, val_s - z_a, nz, nz_end, b_bytes, ldb_bytes, col_ok, G, acc,
                                                    [&](uint32_t k) {
                                                        while (k >= row_end) close_row();
                                                        dirty = true;

@@ -19,6 +19,7 @@ static const void *rk()
 //   2: CTAs of up to 256 threads, 3 per SM (<= 85 registers)
 //   3: (retired: 4 CTAs of 256 threads at <= 64 registers spilled and measured slower; runs as 2)
 //   4: flavour 2 with scalar (one LDS per entry) instead of LDS.128 reads of col_idx / values
+//   5, 6: one CTA of up to 768 threads per SM (<= 85 registers), LDS.128 / scalar reads
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
 // G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
 // `multi` (scatter of C rows to peer GPUs) exists for the default flavour of every shape and for the unstaged one.
@@ -36,6 +37,8 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
             case 1: return rk<T, V, 32, NT, true, U2, 512, 1>();
             case 2: return rk<T, V, 32, NT, true, U1, 256, 3>();
             case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // flavour 2 with scalar A-stream reads
+            case 5: return rk<T, V, 32, NT, true, U1, 768, 1>();               // ONE CTA of 24 warps per SM (24 adjacent lines share L1)
+            case 6: return rk<T, V, 32, NT, true, U1, 768, 1, true, false>();  //   " with scalar A-stream reads
         }
         return rk<T, V, 32, NT, true, U1, 512, 1>();
     }
