@@ -165,38 +165,44 @@ template <> struct VecT<float, 1> { using type = float; };
 template <> struct VecT<float, 2> { using type = float2; };
 template <> struct VecT<float, 4> { using type = float4; };
 
-// read-only (non-coherent) global loads of one lane's vector; `na` = do not allocate in L1
-__device__ __forceinline__ double ldg_na(const double *p)
+// read-only (non-coherent) global loads of one lane's vector with an L2 eviction-priority hint
+__device__ __forceinline__ double ldg_hint(const double *p, uint64_t pol)
 {
     double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ double2 ldg_na(const double2 *p)
+__device__ __forceinline__ double2 ldg_hint(const double2 *p, uint64_t pol)
 {
     double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ float ldg_na(const float *p)
+__device__ __forceinline__ float ldg_hint(const float *p, uint64_t pol)
 {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ float2 ldg_na(const float2 *p)
+__device__ __forceinline__ float2 ldg_hint(const float2 *p, uint64_t pol)
 {
     float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ float4 ldg_na(const float4 *p)
+__device__ __forceinline__ float4 ldg_hint(const float4 *p, uint64_t pol)
 {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
     return v;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 
 template <typename T, int V> struct Lane {
@@ -207,9 +213,14 @@ template <typename T, int V> struct Lane {
 #pragma unroll
         for (int i = 0; i < V; ++i) x[i] = T(0);
     }
-    __device__ __forceinline__ void load(const T *p, bool no_alloc)
+    // HINT: carry an L2 eviction-priority policy (createpolicy) on the read-only load
+    template <bool HINT> __device__ __forceinline__ void load(const T *p, uint64_t pol)
     {
-        VT v = no_alloc ? ldg_na(reinterpret_cast<const VT *>(p)) : __ldg(reinterpret_cast<const VT *>(p));
+        VT v;
+        if constexpr (HINT)
+            v = ldg_hint(reinterpret_cast<const VT *>(p), pol);
+        else
+            v = __ldg(reinterpret_cast<const VT *>(p));
         *reinterpret_cast<VT *>(x) = v;
     }
     __device__ __forceinline__ void load_plain(const T *p) { *reinterpret_cast<VT *>(x) = *reinterpret_cast<const VT *>(p); }

@@ -134,12 +134,9 @@ __global__ void __launch_bounds__(256) spmm_merge_kernel(const MergeParams p)
     };
 
     // stored order inside the chunk, FMA; rows (possibly empty) that end before an entry are closed first
-#ifdef BSM_MERGE_SCALAR_A
-    constexpr bool kVecA = false;
-#else
-    constexpr bool kVecA = true;
-#endif
-    stream_entries<T, V, NT, FULLN, U, kVecA, true, false>(idx_s - z_a, val_s - z_a, nz, nz_end, b_bytes, ldb_bytes, col_ok, G, acc,
+    // LDS.128 reads of the staged A stream (same-box A/B: 3.17 vs 4.16 ms scalar on R-MAT f64) and evict_last
+    // on the B gathers (3.17 -> 3.07 ms): profiles/r1_ab2_rmat_f64_areads.jsonl, r1_ab3_evict_last.jsonl
+    stream_entries<T, V, NT, FULLN, U, true, true, false, true>(idx_s - z_a, val_s - z_a, nz, nz_end, b_bytes, ldb_bytes, col_ok, G, acc,
                                                    [&](uint32_t k) {
                                                        while (k >= row_end) close_row();
                                                        dirty = true;

@@ -88,7 +88,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             ++rr;
             row_end = rp[min(rr + 1u, nr)];
         };
-        stream_entries<T, V, NT, FULLN, U, VECA, false, false>(ci, va, s_all, e_all, b_bytes, ldb_bytes, col_ok, G, acc, [&](uint32_t k) {
+        stream_entries<T, V, NT, FULLN, U, VECA, false, false, false>(ci, va, s_all, e_all, b_bytes, ldb_bytes, col_ok, G, acc, [&](uint32_t k) {
             while (k == row_end) close_row();
         });
         while (rr < nr) close_row();   // the last row with entries, then trailing empty rows
@@ -99,7 +99,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             Lane<T, V> acc[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) acc[t].zero();
-            stream_entries<T, V, NT, FULLN, U, VECA, false, true>(ci, va, s, e, b_bytes, ldb_bytes, col_ok, G, acc, [](uint32_t) {});
+            stream_entries<T, V, NT, FULLN, U, VECA, false, true, false>(ci, va, s, e, b_bytes, ldb_bytes, col_ok, G, acc, [](uint32_t) {});
             const size_t crow = (size_t)(row0 + r) * ldc_bytes;
 #pragma unroll
             for (int t = 0; t < NT; ++t)
