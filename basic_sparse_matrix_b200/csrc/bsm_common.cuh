@@ -6,7 +6,7 @@
 #include <stddef.h>
 #include <string>
 
-#include "../../include/bsm.h"
+#include "bsm.h"   // include/bsm.h (-I../../include here; next to the sources in the Rust crate)
 
 namespace bsm {
 

@@ -76,11 +76,13 @@ typedef struct bsm_tuning {
     uint32_t flags;          /* BSM_TUNE_* (0 = BSM_TUNE_DEFAULT_FLAGS); bit31 set = take literally */
     int32_t rows_per_warp;   /* vector kernel: consecutive rows a warp owns inside a CTA's
                                 super-batch (0 = heuristic: the matrix's dominant row stride)       */
-    int32_t prefer_wide_rows;/* 1: full warp per row even when 128-bit loads need fewer lanes       */
+    int32_t prefer_wide_rows;/* vector kernel: 1 = a full warp per row even when 128-bit loads need fewer
+                                lanes; merge-path does that by default, -1 turns it off there       */
     int32_t reg_flavour;     /* vector kernel: register-budget variant. 0 = heuristic; 1 = CTAs of <= 512
                                 threads, 1 per SM; 2 = same with a gather window twice as deep;
                                 3 = CTAs of <= 256 threads, 3 per SM; 4 = retired (runs as 3);
-                                5 = 3 with scalar instead of LDS.128 reads of col_idx / values
+                                5 = 3 with scalar instead of LDS.128 reads of col_idx / values;
+                                6 / 7 = one CTA of <= 768 threads per SM, LDS.128 / scalar reads
                                 (see csrc/spmm_rows_inst.cuh)                                        */
     int32_t reserved[5];
 } bsm_tuning;

@@ -6,13 +6,14 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
     let nvcc = format!("{cuda}/bin/nvcc");
-    let sources = ["bsm_api.cu", "spmm_rows.cu", "spmm_merge.cu", "convert.cu", "gen.cu", "bsm_nccl.cu"];
+    let sources = ["bsm_api.cu", "spmm_rows.cu", "spmm_rows_f64.cu", "spmm_rows_f32.cu", "spmm_merge.cu", "convert.cu", "gen.cu",
+                   "bsm_nccl.cu"];
     let mut objects = Vec::new();
     for src in sources {
         let obj = out.join(format!("{src}.o"));
         let status = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-                   "-Xcompiler", "-fPIC", "-c"])
+                   "-Xcompiler", "-fPIC", "-Icsrc", "-c"])
             .arg(format!("csrc/{src}"))
             .arg("-o").arg(&obj)
             .status()
@@ -30,7 +31,7 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=nccl");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    println!("cargo:rerun-if-changed=csrc/bsm_common.cuh");
-    println!("cargo:rerun-if-changed=csrc/kernels.h");
-    println!("cargo:rerun-if-changed=csrc/bsm.h");
+    for hdr in ["bsm_common.cuh", "kernels.h", "spmm_stream.cuh", "spmm_rows_kernel.cuh", "spmm_rows_inst.cuh", "bsm.h"] {
+        println!("cargo:rerun-if-changed=csrc/{hdr}");
+    }
 }

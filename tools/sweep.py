@@ -2,7 +2,7 @@
 """tools/sweep.py — time bsm_spmm_tuned over a list of tuning points on ONE resident workload.
 
     python tools/sweep.py --workload laplace3d_256_n128_f64 --steps 10 \
-        --points "col_tile=64;col_tile=64,sync_rows=-1;..."  [--algo vector]
+        --points "col_tile=64;reg_flavour=5,rows_per_slice=32;..."  [--algo vector] [--slice p/N]
 
 Each point is `k=v,k=v` over the fields of bsm_tuning (include/bsm.h); an empty point is the
 library heuristics. Prints one JSON line per point (ms, GFLOP/s, effective GB/s, fraction of the
