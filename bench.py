@@ -306,6 +306,32 @@ def cpu_reference_sample(kind, prm, n, dtype, budget_s, b_host_cols=None, fixed_
     return gf, t, nr, nnz, desc
 
 
+def cpu_lean_parallel_sample(kind, prm, n, dtype, nrows, b_host_cols=None):
+    """NOT the reference — context only: the same contraction in the same order on ALL host threads, dense
+    output, no per-row allocation (oracle/ref_cpu.c ocsr_time_lean_parallel_*), on a row sample."""
+    from basic_sparse_matrix_b200 import gen
+    from oracle.ref_cpu import OracleCsr
+    g = prm["g"]
+    gz = g if kind == "laplace3d" else 1
+    rows_total = g * g * gz
+    reach = g * g if kind == "laplace3d" else g
+    start = (rows_total // 2) // reach * reach
+    r0, r1 = start, min(rows_total, start + nrows)
+    v, ci, ri, _ = gen.laplacian(g, g, gz, r0, r1, dtype)
+    cmin, cmax = int(ci.min()), int(ci.max()) + 1
+    if b_host_cols is not None:
+        cols = [c[cmin:cmax] for c in b_host_cols]
+    else:
+        blk = gen.dense_rows(rows_total, n, 5, gen.MODE_EXACT, 0.0, dtype, row_ids=np.arange(cmin, cmax))
+        cols = [np.ascontiguousarray(blk[:, c]) for c in range(n)]
+    a = OracleCsr.from_raw((r1 - r0, cmax - cmin), v, ci - np.uint64(cmin), ri)
+    t, threads, _ = a.time_lean_parallel(cols, 0, r1 - r0)
+    nnz = int(ri[-1])
+    return {"value": round(2.0 * nnz * n / t / 1e9, 3), "unit": "GFLOP/s", "cores": threads, "seconds": round(t, 3),
+            "sample_rows": r1 - r0, "note": "NOT the reference: lean multi-threaded variant of the same sum (dense output, "
+                                            "no per-row allocation), for context"}
+
+
 def main_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle/ C port; the
     Rust original cannot be built here), rank 0 only."""
@@ -568,6 +594,10 @@ def main():
         gf, t, nr, nnz_s, desc = cpu_reference_sample(kind, prm, n, dtype, 12.0, b_host_cols=host_cols)
         cpu = {"value": round(gf, 5), "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": desc,
                "seconds": round(t, 2), "host_cores_available": os.cpu_count()}
+        try:
+            cpu["lean_all_cores"] = cpu_lean_parallel_sample(kind, prm, n, dtype, 1 << 20, b_host_cols=host_cols)
+        except Exception as ex:
+            cpu["lean_all_cores"] = {"error": str(ex)[:200]}
 
     # ---- free the headline operands, then the secondary workloads (N=1 only) ----------------------------
     for h in (A, B, C):

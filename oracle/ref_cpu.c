@@ -112,3 +112,57 @@ double oracle_now(void)
     }
 DEFINE_TIMED(f64, double)
 DEFINE_TIMED(f32, float)
+
+/* NOT the reference: a "lean" multi-threaded variant for context next to the reference's number —
+ * same arithmetic (stored order, multiply then add) and the same column-major gather, but rows are
+ * split over POSIX threads, the product is written densely (row-major) and nothing is allocated per
+ * row. Returns elapsed seconds. */
+#include <pthread.h>
+#define DEFINE_LEAN(SFXX, TT)                                                                          \
+    typedef struct {                                                                                   \
+        const ocsr_##SFXX *a;                                                                          \
+        const TT *const *rhs_cols;                                                                     \
+        size_t ncols, row_begin, r0, r1;                                                               \
+        TT *out;                                                                                       \
+    } lean_job_##SFXX;                                                                                 \
+    static void *lean_worker_##SFXX(void *arg)                                                         \
+    {                                                                                                  \
+        const lean_job_##SFXX *j = (const lean_job_##SFXX *)arg;                                       \
+        for (size_t r = j->r0; r < j->r1; ++r) {                                                       \
+            const size_t s = j->a->row_index[r], e = j->a->row_index[r + 1];                           \
+            for (size_t c = 0; c < j->ncols; ++c) {                                                    \
+                TT value = (TT)0;                                                                      \
+                const TT *col = j->rhs_cols[c];                                                        \
+                for (size_t k = s; k < e; ++k) {                                                       \
+                    TT prod = j->a->v[k] * col[j->a->col_index[k]];                                    \
+                    value = value + prod;                                                              \
+                }                                                                                      \
+                j->out[(r - j->row_begin) * j->ncols + c] = value;                                     \
+            }                                                                                          \
+        }                                                                                              \
+        return NULL;                                                                                   \
+    }                                                                                                  \
+    double ocsr_time_lean_parallel_##SFXX(const ocsr_##SFXX *a, const TT *const *rhs_cols, size_t rhs_col_count, \
+                                          size_t row_begin, size_t row_end, TT *out_rowmajor, int threads)       \
+    {                                                                                                  \
+        if (threads < 1) threads = 1;                                                                  \
+        if (threads > 256) threads = 256;                                                              \
+        pthread_t tid[256];                                                                            \
+        lean_job_##SFXX job[256];                                                                      \
+        const size_t rows = row_end - row_begin;                                                       \
+        double t0 = oracle_now();                                                                      \
+        for (int t = 0; t < threads; ++t) {                                                            \
+            job[t].a = a;                                                                              \
+            job[t].rhs_cols = rhs_cols;                                                                \
+            job[t].ncols = rhs_col_count;                                                              \
+            job[t].row_begin = row_begin;                                                              \
+            job[t].r0 = row_begin + rows * (size_t)t / (size_t)threads;                                \
+            job[t].r1 = row_begin + rows * (size_t)(t + 1) / (size_t)threads;                          \
+            job[t].out = out_rowmajor;                                                                 \
+            pthread_create(&tid[t], NULL, lean_worker_##SFXX, &job[t]);                                \
+        }                                                                                              \
+        for (int t = 0; t < threads; ++t) pthread_join(tid[t], NULL);                                  \
+        return oracle_now() - t0;                                                                      \
+    }
+DEFINE_LEAN(f64, double)
+DEFINE_LEAN(f32, float)

@@ -253,6 +253,20 @@ class OracleCsr:
             raise RuntimeError(MATERR[rc])
         return out
 
+    def time_lean_parallel(self, rhs_columns, row_begin, row_end, threads=None):
+        """NOT the reference: (seconds, threads, row-major product) of the lean multi-threaded variant (same
+        arithmetic order, rows split over `threads` POSIX threads, dense output, no per-row allocation)."""
+        assert self._sfx in ("f32", "f64")
+        threads = int(threads or os.cpu_count() or 1)
+        ncols = len(rhs_columns)
+        arr, keep = _colptrs(rhs_columns, self._sfx)
+        out = np.empty((row_end - row_begin, ncols), np.float64 if self._sfx == "f64" else np.float32)
+        f = getattr(lib(), f"ocsr_time_lean_parallel_{self._sfx}")
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, type(arr), C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int]
+        t = f(self._h, arr, ncols, row_begin, row_end, out.ctypes.data_as(C.c_void_p), threads)
+        return t, threads, out
+
     def time_mul_dense_rows(self, rhs_columns, row_begin, row_end, faithful=True, rhs_row_count=None):
         """Seconds for the faithful multiply of rows [row_begin,row_end) (CPU baseline leg).
         ``rhs_row_count`` overrides the row count used by the dims check (sparse.rs:427-429) when the
