@@ -884,12 +884,14 @@ static int mul_vector(const bsm_csr *a, int dtype, const T *rhs, uint64_t rhs_le
 }
 
 template <typename CountFn, typename FillFn>
-static int gen_counted(int dtype, uint64_t rows, uint64_t cols, CountFn count_fn, FillFn fill_fn, bsm_csr **out)
+static int gen_counted(int dtype, uint64_t rows, uint64_t cols, uint64_t max_per_row, CountFn count_fn, FillFn fill_fn, bsm_csr **out)
 {
     BSM_TRY(ensure_init());
     if (!out) return fail(BSM_ERR_INVALID_ARGUMENT, "gen: null out");
     if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "gen: dtype must be f32 or f64");
     if (rows >= 0xFFFFFFF0ull) return fail(BSM_ERR_INDEX_OVERFLOW, "gen: too many rows");
+    // the row counts are scanned in u32: refuse anything whose entry count could wrap
+    if ((__uint128_t)rows * max_per_row >= 0xFFFFFFF0ull) return fail(BSM_ERR_INDEX_OVERFLOW, "gen: nnz would not fit the device's u32 indices");
     cudaStream_t sm = g_rt.stream;
     uint32_t *counts = nullptr;
     bsm_csr *a = nullptr;
@@ -1396,7 +1398,7 @@ int bsm_gen_laplacian(int dtype, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t
     const uint64_t n = nx * ny * nz;
     if (row_begin > row_end || row_end > n) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_laplacian: bad row range");
     return gen_counted(
-        dtype, row_end - row_begin, n,
+        dtype, row_end - row_begin, n, 1 + 2 * ((nx > 1) + (ny > 1) + (nz > 1)),
         [&](uint32_t *counts, cudaStream_t sm) { return launch_laplacian_counts(nx, ny, nz, row_begin, row_end, counts, sm); },
         [&](bsm_csr *a, cudaStream_t sm) {
             return launch_laplacian_fill(dtype, nx, ny, nz, row_begin, row_end, a->row_ptr, a->col_idx, a->vals, sm);
@@ -1408,7 +1410,7 @@ int bsm_gen_band(int dtype, uint64_t n, uint64_t hb, uint64_t row_begin, uint64_
 {
     if (n == 0 || row_begin > row_end || row_end > n) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_band: bad arguments");
     return gen_counted(
-        dtype, row_end - row_begin, n,
+        dtype, row_end - row_begin, n, 2 * hb + 1,
         [&](uint32_t *counts, cudaStream_t sm) { return launch_band_counts(n, hb, row_begin, row_end, counts, sm); },
         [&](bsm_csr *a, cudaStream_t sm) {
             return launch_band_fill(dtype, n, hb, row_begin, row_end, a->row_ptr, a->col_idx, a->vals, sm);

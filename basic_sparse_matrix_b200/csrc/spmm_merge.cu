@@ -164,7 +164,8 @@ constexpr uint32_t kFixupSerialMax = 64;   // longer runs go to the cooperative 
 template <typename T>
 __global__ void __launch_bounds__(256) merge_fixup_kernel(const MergeParams p)
 {
-    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // (warp index, not thread index: rows * 32 exceeds 2^32 above 134 M rows)
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (row >= p.rows) return;
     const uint32_t c = (__ldg(p.row_ptr + row) + row) / p.items;

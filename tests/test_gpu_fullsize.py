@@ -226,3 +226,32 @@ def test_config4_checksum_of_checksums_full(gpu):
     rhs = gpu.DeviceCsr.from_host(colsum_row).mul_dense(b).to_rowmajor()   # (1^T A) B
     assert_bitwise(lhs, rhs, "checksum of checksums")
     assert np.abs(lhs).max() > 0
+
+
+def test_near_the_u32_index_limit(gpu):
+    """Maximum sizes: a 3-D Laplacian on a 750^3 grid — 421 875 000 rows, 2.95 G stored entries, i.e. entry
+    indices far above 2^31 and rows + nnz just under 2^32 — through BOTH kernels, two columns, exact-mode
+    data; sampled rows (first, last, random) bit-exact against the oracle. And one size up is refused."""
+    g, n = 750, 2
+    rows = g ** 3
+    a = gpu.DeviceCsr.laplacian(g, g, g)
+    info = a.info()
+    assert info["nnz"] == 7 * rows - 6 * g * g and info["nnz"] > (1 << 31) and rows + info["nnz"] < (1 << 32) - 16
+    b = gpu.DeviceDense.generate(rows, n, seed=9, mode=gen.MODE_EXACT)
+    ids = sample_rows(np.random.default_rng(12), rows, extra=[g * g, rows - g * g - 1, rows // 2])
+    want = []
+    for r in ids:
+        rv, rc, rr, _ = gen.laplacian(g, g, g, int(r), int(r) + 1)
+        bsub = gen.dense_rows(rows, n, 9, gen.MODE_EXACT, row_ids=rc)
+        want.append(ref_numpy.mul_dense_rowmajor(rv, np.arange(len(rc), dtype=np.uint64), rr, bsub)[0])
+    want = np.stack(want)
+    for algo, code in (("vector", _lib.ALGO_VECTOR), ("merge", _lib.ALGO_MERGE)):
+        c = a.mul_dense(b, algo=algo)
+        assert gpu.last_launch_info()["algo"] == code
+        assert_bitwise(rows_of(c, ids, gpu), want, f"near-limit {algo}")
+        c.close()
+    a.close()
+    b.close()
+    with pytest.raises(_lib.BsmError) as e:
+        gpu.DeviceCsr.laplacian(900, 900, 900)          # 5.1 G entries: does not fit u32 indices
+    assert e.value.status == _lib.BSM_ERR_INDEX_OVERFLOW
