@@ -369,3 +369,31 @@ def test_scatter_variant_writes_every_destination(gpu, dtype, n):
     assert e2.value.status == _lib.BSM_ERR_NOT_SUPPORTED
     for h in fulls + [a, bd]:
         h.close()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("algo", ["vector", "merge"])
+def test_borrowed_strided_operands(gpu, dtype, algo):
+    """B and C as borrowed views with a leading dimension larger than the column count and an odd
+    column offset (16-byte alignment broken): the lane shape must fall back to narrower loads and the
+    product must still be bit-exact (dyadic data, so merge-path too); padding columns stay untouched."""
+    rng = np.random.default_rng(44)
+    m, k = 300, 257
+    s = np.dtype(dtype).itemsize
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=5, exact=True)
+    a = gpu.DeviceCsr.from_host(host_csr((m, k), v, ci, ri))
+    for n, ld, off in ((64, 69, 3), (32, 40, 1), (7, 16, 0), (128, 128 + 2, 2)):
+        b_full = random_dense(rng, k, ld, dtype, exact=True)
+        c_full = np.full((m, ld), -3.5, dtype)
+        bd, cd = gpu.DeviceDense.from_rowmajor(b_full), gpu.DeviceDense.from_rowmajor(c_full)
+        bi, cinfo = bd.info(), cd.info()
+        bv = gpu.DeviceDense.borrow(bi["ptr"] + off * s, k, n, bi["ld"], dtype)
+        cv = gpu.DeviceDense.borrow(cinfo["ptr"] + off * s, m, n, cinfo["ld"], dtype)
+        a.mul_dense(bv, out=cv, algo=algo)
+        got = cd.to_rowmajor()
+        want = ref_numpy.mul_dense_rowmajor(v, ci, ri, np.ascontiguousarray(b_full[:, off:off + n]))
+        assert_bitwise(got[:, off:off + n], want, f"strided {algo} n={n} ld={ld} off={off}")
+        assert np.all(got[:, :off] == -3.5) and np.all(got[:, off + n:] == -3.5)
+        for h in (bv, cv, bd, cd):
+            h.close()
+    a.close()
