@@ -35,7 +35,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "SpMM GFLOP/s (2*nnz*ncols; with effective HBM GB/s and fraction of the measured HBM roofline)"
+def _baseline_metric():
+    """BASELINE.json's metric string, verbatim (value = its GFLOP/s part, 2*nnz*ncols / t; the effective GB/s
+    and roofline fraction it also names are the `effective_gbs` / `roofline` keys of the same line)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    except Exception:
+        return "SpMM GFLOP/s + effective HBM GB/s (% roofline) at 1/2/4/8 B200 vs Rust CPU"
+
+
+METRIC = _baseline_metric()
 
 WORKLOADS = {
     # name: (kind, params, n, dtype)
