@@ -20,6 +20,7 @@ static const void *rk()
 //   3: (retired: 4 CTAs of 256 threads at <= 64 registers spilled and measured slower; runs as 2)
 //   4: flavour 2 with scalar (one LDS per entry) instead of LDS.128 reads of col_idx / values
 //   5, 6: one CTA of up to 768 threads per SM (<= 85 registers), LDS.128 / scalar reads
+//   7: flavour 6 with a window of 10 gathers when a lane holds one register tile (else flavour 4)
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
 // G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
 // `multi` (scatter of C rows to peer GPUs) exists for the default flavour of every shape and for the unstaged one.
@@ -39,6 +40,9 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
             case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // flavour 2 with scalar A-stream reads
             case 5: return rk<T, V, 32, NT, true, U1, 768, 1>();               // ONE CTA of 24 warps per SM (24 adjacent lines share L1)
             case 6: return rk<T, V, 32, NT, true, U1, 768, 1, true, false>();  //   " with scalar A-stream reads
+            case 7:   // one tile per lane: window of 10 gathers — as deep as 85 registers allow without spilling
+                if constexpr (NT == 1) return rk<T, V, 32, NT, true, 10, 768, 1, true, false>();
+                else return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // (deeper windows measured slower with several tiles)
         }
         return rk<T, V, 32, NT, true, U1, 512, 1>();
     }

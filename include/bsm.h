@@ -82,7 +82,8 @@ typedef struct bsm_tuning {
                                 threads, 1 per SM; 2 = same with a gather window twice as deep;
                                 3 = CTAs of <= 256 threads, 3 per SM; 4 = retired (runs as 3);
                                 5 = 3 with scalar instead of LDS.128 reads of col_idx / values;
-                                6 / 7 = one CTA of <= 768 threads per SM, LDS.128 / scalar reads
+                                6 / 7 = one CTA of <= 768 threads per SM, LDS.128 / scalar reads;
+                                8 = 7 with a window of 10 gathers (one register tile per lane)
                                 (see csrc/spmm_rows_inst.cuh)                                        */
     int32_t reserved[5];
 } bsm_tuning;
