@@ -124,6 +124,45 @@ def test_vector_tuning_variants_are_bitwise_identical(gpu, dtype):
         assert_bitwise(got, want, f"tuning {tune}")
 
 
+def _near_diagonal_csr(rng, m, k, dtype):
+    """Rows mixing the tridiagonal part (columns row-1, row, row+1 — each present with probability 0.8,
+    so every hit / miss / re-install sequence of the neighbour-row reuse occurs), far columns on both
+    sides, repeated columns, unsorted rows and empty rows."""
+    vals, cols, ri = [], [], [0]
+    for r in range(m):
+        kind = rng.integers(0, 10)
+        row = []
+        if kind > 0:                                            # kind 0: empty row
+            row += [c for c in (r - 1, r, r + 1) if 0 <= c < k and rng.random() < 0.8]
+            row += rng.integers(0, k, size=rng.integers(0, 5)).tolist()
+            if kind == 1 and row:
+                row += [row[0], row[-1]]                        # repeated columns
+            row = sorted(row) if kind < 8 else list(rng.permutation(row))
+        cols += row
+        vals += rng.standard_normal(len(row)).tolist()
+        ri.append(len(cols))
+    return np.array(vals, dtype), np.array(cols, np.uint64), np.array(ri, np.uint64)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vector_neighbour_row_reuse_is_bitwise_identical(gpu, dtype):
+    """reg_flavour 9 / 10: B rows of columns row and row+1 are kept in registers for the next rows
+    (stream_entries_reuse). Same stored-order unfused sum -> bit-exact for ANY matrix, structured or not."""
+    rng = np.random.default_rng(77)
+    m = k = 3001
+    per16 = 16 // np.dtype(dtype).itemsize
+    shapes = [32 * per16, 64 * per16, 32 * per16 // 2, 128 * per16]   # one tile, two tiles, narrower vectors, four tiles (falls back)
+    mats = [_near_diagonal_csr(rng, m, k, dtype), random_csr(rng, m, k, dtype, mean_len=6)]
+    for v, ci, ri in mats:
+        for n in shapes:
+            b = random_dense(rng, k, n, dtype)
+            want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+            for tune in (dict(reg_flavour=9), dict(reg_flavour=10), dict(reg_flavour=9, rows_per_slice=4, rows_per_warp=8),
+                         dict(reg_flavour=10, rows_per_slice=64, stages=2, warps_per_cta=3)):
+                got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", **tune)
+                assert_bitwise(got, want, f"reuse n={n} {tune} launched {info['reg_flavour']}")
+
+
 def test_vector_slow_path_rows_longer_than_a_stage(gpu):
     rng = np.random.default_rng(9)
     m, k, n = 64, 5000, 32
