@@ -434,17 +434,15 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // defaults for full-width shapes, from the same-box A/B sweeps in profiles/: several register tiles per
         // lane -> 3 CTAs x 8 warps per SM; one tile per lane -> one CTA of 24 warps (24 adjacent lines share
         // L1); scalar A-stream reads in both (LDS.128 reads measured 5-8 % slower)
-        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 10) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 7) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
+        int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 8) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 7) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
         if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
         if (flavour == 3) flavour = 2;   // retired flavour
         if (flavour == 7 && sh.NT >= 2) flavour = 4;   // the deep window exists for one tile per lane only
-        if ((flavour == 8 || flavour == 9) && sh.NT >= 4) flavour = 4;   // no reuse variant with four tiles per lane
         if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;       // the scatter variant exists for the default flavours
         // threads per CTA each flavour was compiled for (spmm_rows_inst.cuh)
-        const bool big_cta = wide_full && (flavour == 5 || flavour == 6 || flavour == 7 || (flavour == 8 && sh.NT == 1) || flavour == 9);   // one CTA per SM
-        const int big_warps = flavour == 9 ? 20 : 24;
-        const int max_warps = big_cta ? big_warps : ((flavour >= 2 && wide_full) ? 8 : 16);
-        if (big_cta && !user_nw) nw = big_warps;
+        const bool big_cta = wide_full && (flavour == 5 || flavour == 6 || flavour == 7);   // one CTA of 24 warps per SM
+        const int max_warps = big_cta ? 24 : ((flavour >= 2 && wide_full) ? 8 : 16);
+        if (big_cta && !user_nw) nw = 24;
         nw = std::min(nw, max_warps);
         p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
         p.flags = flags;
@@ -454,7 +452,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         // hardware limit. If even the smallest slice cannot be staged, col_idx / values are read from
         // global memory instead (unstaged variant).
         const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
-        const int resident = (wide_full && (flavour == 2 || flavour == 4 || (flavour == 8 && sh.NT >= 2))) ? 3 : 1;   // CTAs per SM the flavour targets
+        const int resident = (wide_full && (flavour == 2 || flavour == 4)) ? 3 : 1;   // CTAs per SM the flavour targets
         const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (160 * 1024) / resident);
         const uint32_t window = (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight (U)
         const uint32_t window_f7 = 10u;

@@ -7,10 +7,10 @@ namespace bsm {
 
 constexpr int row_default_u(int NT) { return NT >= 4 ? 2 : (NT == 2 ? 4 : 8); }
 
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true, bool MULTI = false, bool REUSE = false>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true, bool MULTI = false>
 static const void *rk()
 {
-    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI, REUSE>);
+    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI>);
 }
 
 // Register-budget flavours (`flavour` argument of the selectors):
@@ -21,7 +21,6 @@ static const void *rk()
 //   4: flavour 2 with scalar (one LDS per entry) instead of LDS.128 reads of col_idx / values
 //   5, 6: one CTA of up to 768 threads per SM (<= 85 registers), LDS.128 / scalar reads
 //   7: flavour 6 with a window of 10 gathers when a lane holds one register tile (else flavour 4)
-//   8, 9: neighbour-row reuse (two B rows kept in registers for the next rows), 24 / 20 warps per SM
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
 // G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
 // `multi` (scatter of C rows to peer GPUs) exists for the default flavour of every shape and for the unstaged one.
@@ -44,14 +43,6 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
             case 7:   // one tile per lane: window of 10 gathers — as deep as 85 registers allow without spilling
                 if constexpr (NT == 1) return rk<T, V, 32, NT, true, 10, 768, 1, true, false>();
                 else return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // (deeper windows measured slower with several tiles)
-            case 8:   // neighbour-row reuse (stream_entries_reuse) at the occupancy of the defaults (<= 85 registers)
-                if constexpr (NT == 1) return rk<T, V, 32, NT, true, 6, 768, 1, true, false, false, true>();
-                else if constexpr (NT == 2) return rk<T, V, 32, NT, true, 3, 256, 3, true, false, false, true>();
-                else return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // four tiles: no registers left for the keep sets
-            case 9:   // " with 20 warps per SM (<= 102 registers): deeper windows
-                if constexpr (NT == 1) return rk<T, V, 32, NT, true, 10, 640, 1, true, false, false, true>();
-                else if constexpr (NT == 2) return rk<T, V, 32, NT, true, 4, 640, 1, true, false, false, true>();
-                else return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();
         }
         return rk<T, V, 32, NT, true, U1, 512, 1>();
     }
@@ -89,5 +80,8 @@ template <typename T, int V> static const void *row_kernel_select_v(Shape sh, bo
     }
     return nullptr;
 }
+
+// largest CTA (threads) a flavour was compiled for
+inline int row_flavour_max_threads(int flavour) { return flavour >= 2 ? 256 : 512; }
 
 }  // namespace bsm

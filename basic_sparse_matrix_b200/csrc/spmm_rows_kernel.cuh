@@ -53,7 +53,7 @@ __host__ __device__ inline RowSmemLayout row_layout(uint32_t cap, uint32_t R, ui
 // MULTI: every C row is also written to p.n_peers further destinations (the full result buffers of the
 // other GPUs, mapped over NVLink): multiply and all-gather in one kernel, P2P stores instead of a
 // collective. `lane_off` = byte offset of the lane's first column inside a row.
-template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA, bool MULTI, bool REUSE = false>
+template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA, bool MULTI>
 __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t *__restrict__ rp, const uint32_t *__restrict__ ci,
                                               const T *__restrict__ va, uint32_t base, uint32_t row0, uint32_t nr,
                                               const char *__restrict__ b_bytes, char *__restrict__ c_bytes, const bool (&col_ok)[NT],
@@ -88,16 +88,9 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             ++rr;
             row_end = rp[min(rr + 1u, nr)];
         };
-        if constexpr (REUSE) {
-            static_assert(FULLN && !VECA, "neighbour-row reuse: full-width shapes, scalar A-stream reads");
-            stream_entries_reuse<T, V, NT, U>(ci, va, rp, nr, row0, b_bytes, ldb_bytes, G, acc, [&](uint32_t k) {
-                while (k == row_end) close_row();
-            });
-        } else {
-            stream_entries<T, V, NT, FULLN, U, VECA, false, false, false>(ci, va, s_all, e_all, b_bytes, ldb_bytes, col_ok, G, acc, [&](uint32_t k) {
-                while (k == row_end) close_row();
-            });
-        }
+        stream_entries<T, V, NT, FULLN, U, VECA, false, false, false>(ci, va, s_all, e_all, b_bytes, ldb_bytes, col_ok, G, acc, [&](uint32_t k) {
+            while (k == row_end) close_row();
+        });
         while (rr < nr) close_row();   // the last row with entries, then trailing empty rows
     } else {
         // ======== 32/G rows side by side, row by row ========
@@ -124,7 +117,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
 // as entry k has been consumed); MAXT / MINB = launch bounds (threads per CTA, CTAs per SM the register allocation must allow).
 // STAGED = col_idx / values of every slice fit the TMA stage (the host guarantees it from the longest
 // row); the unstaged variant reads them from global memory and stages only the row_ptr windows.
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED, bool VECA = true, bool MULTI = false, bool REUSE = false>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED, bool VECA = true, bool MULTI = false>
 __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -222,7 +215,7 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
                 const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
                 const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
                 if constexpr (STAGED)
-                    process_slice<T, V, G, NT, FULLN, U, VECA, MULTI, REUSE>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
+                    process_slice<T, V, G, NT, FULLN, U, VECA, MULTI>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                                 reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,
                                                                 c_bytes, col_ok, grp, streaming, gl * V * (uint32_t)sizeof(T));
                 else

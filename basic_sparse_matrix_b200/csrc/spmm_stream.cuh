@@ -121,95 +121,4 @@ __device__ __forceinline__ void stream_entries(const uint32_t *__restrict__ ci, 
     }
 }
 
-// The same engine with NEIGHBOUR-ROW REUSE for one flat stream over consecutive rows (G == 32): the B rows
-// of columns `row` and `row + 1` are kept in two register sets after their first use, so the entries at
-// columns row-1 / row of the NEXT rows (the tridiagonal part of a stencil or FEM matrix) are served from
-// registers instead of being gathered again — 7 -> 5 gathers per row of a 3-D 7-point Laplacian. The L1
-// data pipe (not HBM) is the co-limit of that workload, and a gather costs it 4 wavefronts per 512 bytes.
-//   A small state machine runs at ISSUE time, U entries ahead of consumption: it tracks the two columns
-//   the keep registers WILL hold when the entry is consumed, skips the gather on a match, and records per
-//   window slot a 2-bit code (0 gather, 1 / 2 keep set a / b, 3 gather + keep) that the consumer obeys.
-//   Both run over the same entry sequence, so they agree for any matrix; entries are still accumulated
-//   strictly in stored order with the unfused multiply-add -> bit-identical to stream_entries.
-// rp[0..nr] = row_ptr window of the slice, row0 = global index of its first row; on_entry as above.
-template <typename T, int V, int NT, int U, typename OnEntry>
-__device__ __forceinline__ void stream_entries_reuse(const uint32_t *__restrict__ ci, const T *__restrict__ va,
-                                                     const uint32_t *__restrict__ rp, uint32_t nr, uint32_t row0,
-                                                     const char *__restrict__ b_bytes, uint32_t ldb_bytes, int G, Lane<T, V> (&acc)[NT],
-                                                     OnEntry &&on_entry)
-{
-    static_assert(U <= 16, "2 bits per window slot in one register");
-    const uint32_t s = rp[0], e = rp[nr];
-    if (s >= e) return;
-    bool col_ok[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) col_ok[t] = true;
-    Lane<T, V> b[U][NT], keep_a[NT], keep_b[NT];
-    uint32_t codes = 0;
-    uint32_t col_a = 0xFFFFFFFFu, col_b = 0xFFFFFFFFu;   // no column has this index (indices < 2^32 - 16)
-    uint32_t i_rr = 0, i_row = row0, i_end = rp[1];     // row of the entry being issued
-    auto issue = [&](uint32_t k, int u) {
-        while (k == i_end) {
-            ++i_rr;
-            ++i_row;
-            i_end = rp[min(i_rr + 1u, nr)];
-        }
-        const uint32_t c = ci[k];
-        uint32_t code;
-        if (c == col_a) {
-            code = 1u;
-        } else if (c == col_b) {
-            code = 2u;
-        } else {
-            load_brow<T, V, NT, true, false>(b[u], b_bytes, ldb_bytes, c, col_ok, G);
-            code = 0u;
-            if (c - i_row <= 1u) {   // column == row or row + 1: the next rows will ask for it again
-                code = 3u;
-                col_b = col_a;
-                col_a = c;
-            }
-        }
-        codes = (codes & ~(3u << (2 * u))) | (code << (2 * u));
-    };
-    auto consume = [&](uint32_t k, int u) {
-        on_entry(k);
-        const T a = va[k];
-        const uint32_t code = (codes >> (2 * u)) & 3u;
-        if (code == 1u) {
-            fma_row<false, T, V, NT>(acc, keep_a, a);
-        } else if (code == 2u) {
-            fma_row<false, T, V, NT>(acc, keep_b, a);
-        } else {
-            fma_row<false, T, V, NT>(acc, b[u], a);
-            if (code == 3u) {
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    keep_b[t] = keep_a[t];
-                    keep_a[t] = b[u][t];
-                }
-            }
-        }
-    };
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (s + u < e) issue(s + u, u);
-    uint32_t k = s;
-    for (; k + 2 * U <= e; k += U) {   // steady state: no bounds checks
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            consume(k + u, u);
-            issue(k + u + U, u);
-        }
-    }
-    for (; k < e; k += U) {            // drain
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (k + u < e) {
-                consume(k + u, u);
-                if (k + u + U < e) issue(k + u + U, u);
-            }
-        }
-    }
-}
-
 }  // namespace bsm

@@ -145,22 +145,20 @@ def _near_diagonal_csr(rng, m, k, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_vector_neighbour_row_reuse_is_bitwise_identical(gpu, dtype):
-    """reg_flavour 9 / 10: B rows of columns row and row+1 are kept in registers for the next rows
-    (stream_entries_reuse). Same stored-order unfused sum -> bit-exact for ANY matrix, structured or not."""
+def test_vector_near_diagonal_rows_all_flavours_bitwise(gpu, dtype):
+    """Stencil-like structure with every irregularity mixed in (missing neighbours, repeated and unsorted
+    columns, empty rows), through every register flavour of the full-width shapes."""
     rng = np.random.default_rng(77)
     m = k = 3001
     per16 = 16 // np.dtype(dtype).itemsize
-    shapes = [32 * per16, 64 * per16, 32 * per16 // 2, 128 * per16]   # one tile, two tiles, narrower vectors, four tiles (falls back)
-    mats = [_near_diagonal_csr(rng, m, k, dtype), random_csr(rng, m, k, dtype, mean_len=6)]
-    for v, ci, ri in mats:
-        for n in shapes:
-            b = random_dense(rng, k, n, dtype)
-            want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
-            for tune in (dict(reg_flavour=9), dict(reg_flavour=10), dict(reg_flavour=9, rows_per_slice=4, rows_per_warp=8),
-                         dict(reg_flavour=10, rows_per_slice=64, stages=2, warps_per_cta=3)):
-                got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", **tune)
-                assert_bitwise(got, want, f"reuse n={n} {tune} launched {info['reg_flavour']}")
+    v, ci, ri = _near_diagonal_csr(rng, m, k, dtype)
+    for n in (32 * per16, 64 * per16, 32 * per16 // 2, 128 * per16):   # one, two tiles per lane, narrower vectors, four tiles
+        b = random_dense(rng, k, n, dtype)
+        want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+        for tune in (dict(), dict(reg_flavour=3), dict(reg_flavour=5), dict(reg_flavour=6), dict(reg_flavour=7, rows_per_slice=4, rows_per_warp=8),
+                     dict(reg_flavour=8), dict(reg_flavour=8, rows_per_slice=64, stages=2, warps_per_cta=3)):
+            got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", **tune)
+            assert_bitwise(got, want, f"near-diagonal n={n} {tune} launched {info['reg_flavour']}")
 
 
 def test_vector_slow_path_rows_longer_than_a_stage(gpu):
