@@ -60,6 +60,16 @@ template <typename T, int V, int G> static const void *rk_narrow(bool fulln, int
     return fulln ? rk<T, V, G, 1, true, 8, 512, 1>() : rk<T, V, G, 1, false, 8, 512, 1>();
 }
 
+// G < 32 with several register tiles per lane (lane groups walking their own flat streams): full-width
+// shapes only, scalar A-stream reads, 3 CTAs x 8 warps (flavour 4, the default) or one CTA of 24 warps (6)
+template <typename T, int V, int G, int NT> static const void *rk_grouped(bool fulln, int flavour, bool multi)
+{
+    constexpr int U1 = row_default_u(NT);
+    if (!fulln || multi) return nullptr;
+    if (flavour == 6) return rk<T, V, G, NT, true, U1, 768, 1, true, false>();
+    return rk<T, V, G, NT, true, U1, 256, 3, true, false>();
+}
+
 template <typename T, int V> static const void *row_kernel_select_v(Shape sh, bool fulln, int flavour, bool multi)
 {
     if (sh.G == 32) {
@@ -70,7 +80,24 @@ template <typename T, int V> static const void *row_kernel_select_v(Shape sh, bo
         }
         return nullptr;
     }
-    if (sh.NT != 1) return nullptr;
+    if (sh.NT != 1) {
+        if constexpr (V * sizeof(T) == 16) {   // grouped flat streams: 128-bit lanes only
+            if (sh.NT == 2) {
+                switch (sh.G) {
+                    case 16: return rk_grouped<T, V, 16, 2>(fulln, flavour, multi);
+                    case 8: return rk_grouped<T, V, 8, 2>(fulln, flavour, multi);
+                    case 4: return rk_grouped<T, V, 4, 2>(fulln, flavour, multi);
+                }
+            } else if (sh.NT == 4) {
+                switch (sh.G) {
+                    case 16: return rk_grouped<T, V, 16, 4>(fulln, flavour, multi);
+                    case 8: return rk_grouped<T, V, 8, 4>(fulln, flavour, multi);
+                    case 4: return rk_grouped<T, V, 4, 4>(fulln, flavour, multi);
+                }
+            }
+        }
+        return nullptr;
+    }
     switch (sh.G) {
         case 16: return rk_narrow<T, V, 16>(fulln, flavour, multi);
         case 8: return rk_narrow<T, V, 8>(fulln, flavour, multi);

@@ -64,15 +64,20 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
     const uint32_t ldc_bytes = p.ldc * (uint32_t)sizeof(T);
     ci -= base;   // entry k at ci[k] / va[k]
     va -= base;
-    if constexpr (G == 32) {
-        // ======== one flat entry stream per warp ========
-        const uint32_t s_all = rp[0], e_all = rp[nr];
+    if constexpr (G == 32 || NT > 1) {
+        // ======== one flat entry stream per lane group ========
+        // G == 32: the warp walks the whole slice. G < 32 (several register tiles per lane): the slice is cut
+        // into 32/G runs of consecutive rows, one per lane group — one LDS of col_idx / values then feeds
+        // 32/G rows (the A stream costs the L1 data pipe as much per entry as a quarter of a 512-byte gather).
+        const uint32_t nrg = RPP == 1 ? nr : (nr + RPP - 1) / RPP;
+        const uint32_t g0 = RPP == 1 ? 0u : min(grp * nrg, nr);   // this group's rows [g0, g1) of the slice
+        const uint32_t g1 = RPP == 1 ? nr : min(g0 + nrg, nr);
         Lane<T, V> acc[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t) acc[t].zero();                   // T::default()  sparse.rs:434
-        uint32_t rr = 0;                                               // row being accumulated (slice-local)
-        uint32_t row_end = rp[1];
-        size_t crow = (size_t)row0 * ldc_bytes;   // byte offset of the row inside C (and inside every peer copy)
+        uint32_t rr = g0;                                              // row being accumulated (slice-local)
+        uint32_t row_end = rp[min(g0 + 1u, g1)];
+        size_t crow = (size_t)(row0 + g0) * ldc_bytes;   // byte offset of the row inside C (and inside every peer copy)
         auto close_row = [&]() {
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -86,12 +91,12 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
             }
             crow += ldc_bytes;
             ++rr;
-            row_end = rp[min(rr + 1u, nr)];
+            row_end = rp[min(rr + 1u, g1)];
         };
-        stream_entries<T, V, NT, FULLN, U, VECA, false, false, false>(ci, va, s_all, e_all, b_bytes, ldb_bytes, col_ok, G, acc, [&](uint32_t k) {
+        stream_entries<T, V, NT, FULLN, U, VECA, false, false, false>(ci, va, rp[g0], rp[g1], b_bytes, ldb_bytes, col_ok, G, acc, [&](uint32_t k) {
             while (k == row_end) close_row();
         });
-        while (rr < nr) close_row();   // the last row with entries, then trailing empty rows
+        while (rr < g1) close_row();   // the last row with entries, then trailing empty rows
     } else {
         // ======== 32/G rows side by side, row by row ========
         for (uint32_t r = grp; r < nr; r += RPP) {
@@ -141,11 +146,11 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
     const uint32_t my_supers = blockIdx.x < p.num_super ? (p.num_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     const uint32_t my_slices = my_supers * spw;
 
-    // Two renditions of the slice loop, chosen at compile time. Wide shapes (G == 32) have long slices and
+    // Two renditions of the slice loop, chosen at compile time. Wide shapes (G == 32, or several tiles per lane) have long slices and
     // a tight register budget: the slice position is recomputed from the slice index (measured 3-4 % faster
     // there than cursors). Narrow shapes (G < 32) have short slices — a few row passes — and registers to
     // spare: incremental cursors, no divisions in the loop (SpMV 0.078 -> 0.063 ms).
-    if constexpr (G == 32) {
+    if constexpr (G == 32 || NT > 1) {
         // first row of this warp's i-th slice
         auto slice_row0 = [&](uint32_t i) -> uint64_t {
             const uint32_t k = i / spw, t = i - k * spw;

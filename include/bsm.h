@@ -85,7 +85,11 @@ typedef struct bsm_tuning {
                                 6 / 7 = one CTA of <= 768 threads per SM, LDS.128 / scalar reads;
                                 8 = 7 with a window of 10 gathers (one register tile per lane)
                                 (see csrc/spmm_rows_inst.cuh)                                        */
-    int32_t reserved[5];
+    int32_t lanes_per_row;   /* vector kernel: lanes that share one output row (power of two <= 32). 0 = heuristic.
+                                Fewer lanes than the 128-bit loads need -> 2 or 4 register tiles per lane and
+                                32/lanes rows side by side, each lane group walking its own flat entry stream:
+                                one LDS of the A stream then feeds 32/lanes rows                            */
+    int32_t reserved[4];
 } bsm_tuning;
 
 /* what the last bsm_spmm* call on this thread actually launched */

@@ -161,6 +161,27 @@ def test_vector_near_diagonal_rows_all_flavours_bitwise(gpu, dtype):
             assert_bitwise(got, want, f"near-diagonal n={n} {tune} launched {info['reg_flavour']}")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vector_grouped_lanes_bitwise(gpu, dtype):
+    """lanes_per_row < 32 with 2 or 4 register tiles per lane: 32/G lane groups each walk their own flat
+    entry stream over a run of consecutive rows of the slice (rows of very different lengths side by side,
+    empty groups, slices shorter than the group count)."""
+    rng = np.random.default_rng(91)
+    per16 = 16 // np.dtype(dtype).itemsize
+    for m, k in ((3001, 3001), (5, 40), (1, 9), (67, 500)):
+        mats = [_near_diagonal_csr(rng, m, k, dtype), random_csr(rng, m, k, dtype, mean_len=6, giant_row=min(3, m - 1), giant_len=200)]
+        for mi, (v, ci, ri) in enumerate(mats):
+            for g, nt in ((16, 2), (16, 4), (8, 2), (8, 4), (4, 2), (4, 4)):
+                n = per16 * g * nt
+                b = random_dense(rng, k, n, dtype)
+                want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+                for tune in (dict(), dict(reg_flavour=7), dict(rows_per_slice=8, rows_per_warp=24), dict(rows_per_slice=64, stages=2, warps_per_cta=3)):
+                    got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", lanes_per_row=g, **tune)
+                    if mi == 0:   # (a giant row that cannot be staged falls back to a warp per row — by design)
+                        assert (info["lanes_per_row"], info["reg_tiles"]) == (g, nt), info
+                    assert_bitwise(got, want, f"grouped m={m} n={n} G={g} NT={nt} {tune}")
+
+
 def test_vector_slow_path_rows_longer_than_a_stage(gpu):
     rng = np.random.default_rng(9)
     m, k, n = 64, 5000, 32
