@@ -458,7 +458,9 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             // L1); scalar A-stream reads in both (LDS.128 reads measured 5-8 % slower)
             int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 8) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 7) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
             if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
-            if (grouped) flavour = (tn.reg_flavour == 7 || tn.reg_flavour == 8 || (auto_grouped && tn.reg_flavour <= 0)) ? 6 : 4;   // one CTA of 24 warps, or 3 x 8 warps (default)
+            if (grouped) {
+                flavour = (tn.reg_flavour == 7 || tn.reg_flavour == 8 || (auto_grouped && tn.reg_flavour <= 0)) ? 6 : 4;
+            }   // one CTA of 24 warps, or 3 x 8 warps (default)
             if (flavour == 3) flavour = 2;   // retired flavour
             if (flavour == 7 && sh.NT >= 2) flavour = 4;   // the deep window exists for one tile per lane only
             if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;       // the scatter variant exists for the default flavours
@@ -606,10 +608,31 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
         const uint32_t n = std::min(tile, n_total - col0);
         const uint64_t ldcar = round_up(n, vmax);
         Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows >= 0, ldcar);
+        // fewer lanes per chunk, 2 or 4 register tiles per lane (128-bit lanes, full-width shapes): one LDS.128 of the
+        // staged A stream then feeds 32/G chunks. Defaults from the same-box A/B on R-MAT (profiles/r1_sweepx_rmat_*):
+        // 512-byte rows 16 lanes x 2 tiles, 192 items (3.08 -> 3.01 ms); 256-byte rows 8 lanes x 2 tiles, 160 items
+        // (2.08 -> 1.84 ms, r1_sweepy_rmat_f32)
+        int want_g = tn.lanes_per_row;
+        uint32_t auto_items = 0;
+        if (want_g == 0 && tn.prefer_wide_rows == 0 && tn.merge_items <= 0 && tn.warps_per_cta <= 0) {
+            if ((size_t)n * s == 512) { want_g = 16; auto_items = 192; }
+            if ((size_t)n * s == 256) { want_g = 8; auto_items = 160; }
+        }
+        bool grouped = false;
+        if (want_g > 0) {
+            const Shape sv = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, false, ldcar);
+            const int g = want_g, nt = sv.V * (int)s == 16 ? (int)(n / (uint32_t)(sv.V * g)) : 0;
+            if ((g == 16 || g == 8 || g == 4) && (nt == 2 || nt == 4) && n == (uint32_t)(sv.V * g * nt)) {
+                sh.V = sv.V;
+                sh.G = g;
+                sh.NT = nt;
+                grouped = true;
+            }
+        }
         const int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 8) : 8;
         const int block = nw * 32;
         const uint32_t groups = (uint32_t)nw * (32u / sh.G);
-        uint32_t items = tn.merge_items > 0 ? (uint32_t)tn.merge_items : (sh.G == 32 ? 384u : std::max(16u, 2048u / groups));
+        uint32_t items = tn.merge_items > 0 ? (uint32_t)tn.merge_items : (grouped && auto_items ? auto_items : (sh.G == 32 ? 384u : std::max(16u, 2048u / groups)));
         items = (uint32_t)round_up(items, 4);
         if (total + items >= 0xFFFFFFF0ull) return fail(BSM_ERR_INDEX_OVERFLOW, "spmm_merge: rows+nnz must fit u32");
         const uint32_t num_chunks = (uint32_t)((total + items - 1) / items);

@@ -246,7 +246,27 @@ template <typename T, int V> static const void *merge_kernel_select_gnt(int G, i
         }
         return nullptr;
     }
-    if (NT != 1) return nullptr;
+    if (NT != 1) {
+        // several register tiles per lane on fewer lanes: 32/G chunks side by side per warp, so one LDS of the
+        // staged A stream feeds 32/G entries (128-bit lanes, full-width shapes only)
+        if constexpr (V * sizeof(T) == 16) {
+            if (!fulln) return nullptr;
+            if (NT == 2) {
+                switch (G) {
+                    case 16: return merge_kernel_ptr<T, V, 16, 2>(true);
+                    case 8: return merge_kernel_ptr<T, V, 8, 2>(true);
+                    case 4: return merge_kernel_ptr<T, V, 4, 2>(true);
+                }
+            } else if (NT == 4) {
+                switch (G) {
+                    case 16: return merge_kernel_ptr<T, V, 16, 4>(true);
+                    case 8: return merge_kernel_ptr<T, V, 8, 4>(true);
+                    case 4: return merge_kernel_ptr<T, V, 4, 4>(true);
+                }
+            }
+        }
+        return nullptr;
+    }
     switch (G) {
         case 16: return merge_kernel_ptr<T, V, 16, 1>(fulln);
         case 8: return merge_kernel_ptr<T, V, 8, 1>(fulln);

@@ -217,6 +217,28 @@ def test_merge_within_tolerance_on_real_inputs(gpu, dtype, n):
     assert_tolerance(got, want, scale, TOL[dtype], f"merge real n={n}")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_merge_grouped_lanes(gpu, dtype):
+    """merge-path with lanes_per_row < 32 and 2 or 4 register tiles per lane (32/G chunks side by side per warp):
+    bit-exact on exactly representable data, within tolerance on real data."""
+    rng = np.random.default_rng(404)
+    m, k = 1500, 600
+    per16 = 16 // np.dtype(dtype).itemsize
+    ve, cie, rie = random_csr(rng, m, k, dtype, mean_len=4, empty_frac=0.4, giant_row=777, giant_len=9000, exact=True)
+    vr, cir, rir = random_csr(rng, m, k, dtype, mean_len=6, giant_row=1, giant_len=5000)
+    for g, nt in ((16, 2), (8, 4), (8, 2), (4, 4), (16, 4), (4, 2)):
+        n = per16 * g * nt
+        be = random_dense(rng, k, n, dtype, exact=True)
+        for tune in (dict(), dict(merge_items=96), dict(merge_items=32, warps_per_cta=4)):
+            got, info = gpu_product(gpu, (m, k), ve, cie, rie, be, "merge", lanes_per_row=g, **tune)
+            assert (info["algo"], info["lanes_per_row"], info["reg_tiles"]) == (_lib.ALGO_MERGE, g, nt), info
+            assert_bitwise(got, ref_numpy.mul_dense_rowmajor(ve, cie, rie, be), f"merge grouped exact G={g} NT={nt} {tune}")
+        br = random_dense(rng, k, n, dtype)
+        got, _ = gpu_product(gpu, (m, k), vr, cir, rir, br, "merge", lanes_per_row=g)
+        assert_tolerance(got, ref_numpy.mul_dense_rowmajor(vr, cir, rir, br), ref_numpy.abs_product_sum(vr, cir, rir, br), TOL[dtype],
+                         f"merge grouped real G={g} NT={nt}")
+
+
 def test_merge_items_variants(gpu):
     rng = np.random.default_rng(17)
     m, k, n = 1500, 600, 64
