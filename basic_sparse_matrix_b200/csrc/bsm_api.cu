@@ -401,14 +401,18 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             // (grouped flat streams; exists for full 128-bit shapes only)
             bool grouped = false, auto_grouped = false;
             int want_g = tn.lanes_per_row;
-            // default for one 128-bit tile per lane (n = 32 x 16 bytes) on regular rows: 8 lanes x 4 tiles, four rows
-            // side by side (same-box A/B on the north_star shape, 3-D Laplacian x 64 f64: 4.54 -> 4.04 ms,
-            // profiles/r1_sweepu_l3d_n64.jsonl). Rows of very uneven length stay on the warp-per-row stream,
-            // which balances them inside the warp.
-            if (want_g == 0 && sh.G == 32 && sh.NT == 1 && tn.reg_flavour <= 0 && tn.warps_per_cta <= 0 && tn.prefer_wide_rows == 0 &&
+            // defaults on regular rows (uneven rows stay on the warp-per-row stream, which balances them inside the
+            // warp; same-box A/B on the 3-D Laplacian, profiles/r1_sweep{u,v,w,y,z}_l3d_*.jsonl):
+            //   one 128-bit tile per lane, 512-byte rows (x64 f64): 8 lanes x 4 tiles            4.54 -> 3.92 ms
+            //   256-byte rows (x32 f64, x64 f32), short rows: 16 -> 8 lanes x 2 tiles            4.28 -> 2.22 ms
+            //   128-byte rows (x16 f64), short rows: 8 -> 4 lanes x 2 tiles                      2.70 -> 1.37 ms
+            // (the row-by-row walk of narrow shapes drains its gather window at every row end; rows of ~65 entries,
+            // the band matrix x32 f32, are still faster row by row: 0.45 vs 0.72 ms)
+            if (want_g == 0 && sh.NT == 1 && tn.reg_flavour <= 0 && tn.warps_per_cta <= 0 && tn.prefer_wide_rows == 0 &&
                 (double)a->max_row_nnz <= 4.0 * mean + 8.0) {
-                want_g = 8;
-                auto_grouped = true;
+                if (sh.G == 32) want_g = 8;
+                else if ((sh.G == 16 || sh.G == 8) && mean <= 32.0) want_g = sh.G / 2;
+                auto_grouped = want_g > 0;
             }
             if (allow_grouped && want_g > 0 && want_g < sh.G && !scatter && sh.V * (int)s == 16 && n == (uint32_t)(sh.V * sh.G * sh.NT)) {
                 const int g = want_g, nt = (int)(n / (uint32_t)(sh.V * g));
@@ -446,7 +450,8 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
                 R = (uint32_t)tn.rows_per_slice;
             } else {
                 // measured (profiles/r1_sweepi_*): one register tile per lane (NT = 1) likes ~224-entry slices
-                const double target = (sh.G == 32 && sh.NT == 1) ? 224.0 : 128.0;   // (the grouped default measured best at 16 rows x 2 stages)
+                // (grouped defaults: 8 x 4 tiles measured best at 16 rows x 2 stages, 8 x 2 tiles at 32 rows x 2 stages)
+                const double target = ((sh.G == 32 && sh.NT == 1) || (grouped && auto_grouped && sh.NT == 2)) ? 224.0 : 128.0;
                 R = (uint32_t)std::min<double>(256.0, std::max(1.0, target / std::max(1.0, mean)));
                 if (sh.G < 32) R = std::max(R, 4u * rpp);
             }
@@ -459,7 +464,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 8) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 7) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
             if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
             if (grouped) {
-                flavour = (tn.reg_flavour == 7 || tn.reg_flavour == 8 || (auto_grouped && tn.reg_flavour <= 0)) ? 6 : 4;
+                flavour = (tn.reg_flavour == 7 || tn.reg_flavour == 8 || (auto_grouped && tn.reg_flavour <= 0 && sh.G >= 8)) ? 6 : 4;
             }   // one CTA of 24 warps, or 3 x 8 warps (default)
             if (flavour == 3) flavour = 2;   // retired flavour
             if (flavour == 7 && sh.NT >= 2) flavour = 4;   // the deep window exists for one tile per lane only
@@ -473,7 +478,7 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
                 while (nw > 3 && (uint64_t)nw * R * (uint64_t)g_rt.sm_count > a->rows) nw /= 2;
             }
             nw = std::min(nw, max_warps);
-            p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : (grouped && auto_grouped ? 2u : 3u);
+            p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : (grouped && auto_grouped && sh.G >= 8 ? 2u : 3u);
             p.flags = flags;
             // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start).
             // Shrink, in this order, the ring depth, the slice and the CTA until the rings fit: first under
