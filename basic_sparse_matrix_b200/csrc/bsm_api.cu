@@ -470,7 +470,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             if (flavour == 7 && sh.NT >= 2) flavour = 4;   // the deep window exists for one tile per lane only
             if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;       // the scatter variant exists for the default flavours
             // threads per CTA each flavour was compiled for (spmm_rows_inst.cuh)
-            const bool interleave = grouped && tn.interleave_rows > 0;
             const bool big_cta = (wide_full && (flavour == 5 || flavour == 6 || flavour == 7)) || (grouped && flavour == 6);   // one CTA of 24 warps per SM
             const int max_warps = big_cta ? 24 : ((flavour >= 2 && (wide_full || grouped)) ? 8 : 16);
             if (big_cta && !user_nw) {
@@ -551,12 +550,11 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             p.num_super = (uint32_t)((a->rows + S - 1) / S);
             const int block = nw * 32;
             int occ = 0;
-            const int kflavour = interleave ? flavour + 8 : flavour;   // 12 / 14 = interleaved renditions of 4 / 6
-            BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, kflavour, multi, block, smem, &occ));
+            BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, flavour, multi, block, smem, &occ));
             if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_vector: kernel does not fit on an SM");
             int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
             const int grid = (int)std::min<uint64_t>(p.num_super, (uint64_t)g_rt.sm_count * ctas);
-            if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, kflavour, multi, grid, block, smem, ctas, g_rt.stream));
+            if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, flavour, multi, grid, block, smem, ctas, g_rt.stream));
             g_info.kernels += grid > 0;
             g_info.vec_elems = sh.V;
             g_info.lanes_per_row = sh.G;
@@ -567,7 +565,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             g_info.rows_per_slice = (int)p.R;
             g_info.rows_per_warp = (int)p.P;
             g_info.reg_flavour = flavour + 1;
-            g_info.interleave_rows = interleave ? 1 : 0;
             g_info.stages = (int)p.stages;
             g_info.capacity = (int)p.cap;
             break;

@@ -7,10 +7,10 @@ namespace bsm {
 
 constexpr int row_default_u(int NT) { return NT >= 4 ? 2 : (NT == 2 ? 4 : 8); }
 
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true, bool MULTI = false, bool ILV = false>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true, bool MULTI = false>
 static const void *rk()
 {
-    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI, ILV>);
+    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI>);
 }
 
 // Register-budget flavours (`flavour` argument of the selectors):
@@ -67,9 +67,6 @@ template <typename T, int V, int G, int NT> static const void *rk_grouped(bool f
     constexpr int U1 = row_default_u(NT);
     if (!fulln || multi) return nullptr;
     if (flavour == 6) return rk<T, V, G, NT, true, U1, 768, 1, true, false>();
-    // 12 / 14: flavours 4 / 6 with the rows of a slice interleaved between the lane groups (stream_rows_interleaved)
-    if (flavour == 12) return rk<T, V, G, NT, true, U1, 256, 3, true, false, false, true>();
-    if (flavour == 14) return rk<T, V, G, NT, true, U1, 768, 1, true, false, false, true>();
     return rk<T, V, G, NT, true, U1, 256, 3, true, false>();
 }
 

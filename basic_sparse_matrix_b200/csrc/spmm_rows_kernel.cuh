@@ -53,7 +53,7 @@ __host__ __device__ inline RowSmemLayout row_layout(uint32_t cap, uint32_t R, ui
 // MULTI: every C row is also written to p.n_peers further destinations (the full result buffers of the
 // other GPUs, mapped over NVLink): multiply and all-gather in one kernel, P2P stores instead of a
 // collective. `lane_off` = byte offset of the lane's first column inside a row.
-template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA, bool MULTI, bool ILV = false>
+template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA, bool MULTI>
 __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t *__restrict__ rp, const uint32_t *__restrict__ ci,
                                               const T *__restrict__ va, uint32_t base, uint32_t row0, uint32_t nr,
                                               const char *__restrict__ b_bytes, char *__restrict__ c_bytes, const bool (&col_ok)[NT],
@@ -64,21 +64,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
     const uint32_t ldc_bytes = p.ldc * (uint32_t)sizeof(T);
     ci -= base;   // entry k at ci[k] / va[k]
     va -= base;
-    if constexpr (ILV && G < 32 && NT > 1) {
-        // ======== grouped lanes, rows interleaved between the groups (stream_rows_interleaved) ========
-        static_assert(FULLN && !MULTI, "interleaved grouped streams: full-width shapes, no scatter");
-        Lane<T, V> acc[NT];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) acc[t].zero();
-        stream_rows_interleaved<T, V, NT, U, RPP>(ci, va, rp, nr, grp, b_bytes, ldb_bytes, G, acc, [&](uint32_t r) {
-            const size_t crow = (size_t)(row0 + r) * ldc_bytes;
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                acc[t].store(reinterpret_cast<T *>(c_bytes + crow) + t * G * V, streaming);
-                acc[t].zero();
-            }
-        });
-    } else if constexpr (G == 32 || NT > 1) {
+    if constexpr (G == 32 || NT > 1) {
         // ======== one flat entry stream per lane group ========
         // G == 32: the warp walks the whole slice. G < 32 (several register tiles per lane): the slice is cut
         // into 32/G runs of consecutive rows, one per lane group — one LDS of col_idx / values then feeds
@@ -136,7 +122,7 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
 // as entry k has been consumed); MAXT / MINB = launch bounds (threads per CTA, CTAs per SM the register allocation must allow).
 // STAGED = col_idx / values of every slice fit the TMA stage (the host guarantees it from the longest
 // row); the unstaged variant reads them from global memory and stages only the row_ptr windows.
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED, bool VECA = true, bool MULTI = false, bool ILV = false>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED, bool VECA = true, bool MULTI = false>
 __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -234,11 +220,11 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
                 const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
                 const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
                 if constexpr (STAGED)
-                    process_slice<T, V, G, NT, FULLN, U, VECA, MULTI, ILV>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
+                    process_slice<T, V, G, NT, FULLN, U, VECA, MULTI>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                                 reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,
                                                                 c_bytes, col_ok, grp, streaming, gl * V * (uint32_t)sizeof(T));
                 else
-                    process_slice<T, V, G, NT, FULLN, U, false, MULTI, ILV>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp,
+                    process_slice<T, V, G, NT, FULLN, U, false, MULTI>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp,
                                                                        streaming, gl * V * (uint32_t)sizeof(T));
             }
         }
@@ -348,11 +334,11 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
                 const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
                 const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
                 if constexpr (STAGED)
-                    process_slice<T, V, G, NT, FULLN, U, VECA, MULTI, ILV>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
+                    process_slice<T, V, G, NT, FULLN, U, VECA, MULTI>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                                 reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,
                                                                 c_bytes, col_ok, grp, streaming, gl * V * (uint32_t)sizeof(T));
                 else
-                    process_slice<T, V, G, NT, FULLN, U, false, MULTI, ILV>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp,
+                    process_slice<T, V, G, NT, FULLN, U, false, MULTI>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp,
                                                                        streaming, gl * V * (uint32_t)sizeof(T));
             }
         }

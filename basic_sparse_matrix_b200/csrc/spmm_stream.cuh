@@ -121,70 +121,4 @@ __device__ __forceinline__ void stream_entries(const uint32_t *__restrict__ ci, 
     }
 }
 
-// INTERLEAVED rows for grouped lanes: lane group `grp` of RPP walks the rows grp, grp+RPP, grp+2*RPP, ... of a
-// slice as one stream (rolling window of U gathers that never drains at row ends), so at any moment the RPP
-// groups of a warp work on ADJACENT rows: on a stencil or band matrix their gathers hit adjacent B rows — one
-// contiguous run of RPP rows per instruction, shared through L1 — instead of rows a quarter slice apart.
-// Two cursors (issue, consume) jump from one row's entries to the next row's; `close_row(r)` stores and
-// clears the accumulators of slice-local row r. Stored order, unfused multiply-add: bit-exact.
-template <typename T, int V, int NT, int U, int RPP, typename CloseRow>
-__device__ __forceinline__ void stream_rows_interleaved(const uint32_t *__restrict__ ci, const T *__restrict__ va,
-                                                        const uint32_t *__restrict__ rp, uint32_t nr, uint32_t grp,
-                                                        const char *__restrict__ b_bytes, uint32_t ldb_bytes, int G,
-                                                        Lane<T, V> (&acc)[NT], CloseRow &&close_row)
-{
-    uint32_t total = 0;   // entries of this group's rows
-    for (uint32_t r = grp; r < nr; r += RPP) total += rp[r + 1] - rp[r];
-    uint32_t rr = grp;    // row being accumulated (slice-local)
-    if (total) {
-        bool col_ok[NT];
-#pragma unroll
-        for (int t = 0; t < NT; ++t) col_ok[t] = true;
-        Lane<T, V> b[U][NT];
-        uint32_t k = rp[rr], row_end = rp[rr + 1];          // consume cursor
-        uint32_t irr = rr, ik = k, i_end = row_end;         // issue cursor, U entries ahead
-        auto issue = [&](int u) {                           // only while entries remain: a later row has them
-            while (ik == i_end) {
-                irr += RPP;
-                ik = rp[irr];
-                i_end = rp[irr + 1];
-            }
-            load_brow<T, V, NT, true, false>(b[u], b_bytes, ldb_bytes, ci[ik], col_ok, G);
-            ++ik;
-        };
-        auto consume = [&](int u) {
-            while (k == row_end) {
-                close_row(rr);
-                rr += RPP;
-                k = rp[rr];
-                row_end = rp[rr + 1];
-            }
-            fma_row<false, T, V, NT>(acc, b[u], va[k]);
-            ++k;
-        };
-        uint32_t n_cons = total;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if ((uint32_t)u < total) issue(u);
-        for (; n_cons >= 2 * U; n_cons -= U) {   // steady state: every consumed slot is refilled
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                consume(u);
-                issue(u);
-            }
-        }
-        while (n_cons > 0) {                     // drain
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (n_cons > 0) {
-                    consume(u);
-                    if (n_cons > (uint32_t)U) issue(u);
-                    --n_cons;
-                }
-            }
-        }
-    }
-    for (; rr < nr; rr += RPP) close_row(rr);   // the last row with entries, trailing / all-empty rows
-}
-
 }  // namespace bsm

@@ -89,9 +89,7 @@ typedef struct bsm_tuning {
                                 Fewer lanes than the 128-bit loads need -> 2 or 4 register tiles per lane and
                                 32/lanes rows side by side, each lane group walking its own flat entry stream:
                                 one LDS of the A stream then feeds 32/lanes rows                            */
-    int32_t interleave_rows; /* vector kernel, grouped lanes: 1 = lane group g walks rows g, g+32/lanes, ... of a slice
-                                (adjacent rows side by side) instead of a run of consecutive rows; 0 = heuristic  */
-    int32_t reserved[3];
+    int32_t reserved[4];
 } bsm_tuning;
 
 /* what the last bsm_spmm* call on this thread actually launched */
@@ -107,7 +105,7 @@ typedef struct bsm_launch_info {
     int32_t passes;          /* column-tile passes                                                  */
     int32_t merge_items, merge_chunks;
     int32_t rows_per_warp, reg_flavour, col_tile;
-    int32_t interleave_rows; /* grouped lanes: 1 = rows of a slice interleaved between the lane groups */
+    int32_t reserved[1];
 } bsm_launch_info;
 
 /* ------------------------------------------------------------------------------------------

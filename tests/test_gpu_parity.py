@@ -175,8 +175,7 @@ def test_vector_grouped_lanes_bitwise(gpu, dtype):
                 n = per16 * g * nt
                 b = random_dense(rng, k, n, dtype)
                 want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
-                for tune in (dict(), dict(reg_flavour=7), dict(rows_per_slice=8, rows_per_warp=24), dict(rows_per_slice=64, stages=2, warps_per_cta=3),
-                             dict(interleave_rows=1), dict(interleave_rows=1, reg_flavour=7, rows_per_slice=8), dict(interleave_rows=1, rows_per_slice=20, rows_per_warp=40)):
+                for tune in (dict(), dict(reg_flavour=7), dict(rows_per_slice=8, rows_per_warp=24), dict(rows_per_slice=64, stages=2, warps_per_cta=3)):
                     got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", lanes_per_row=g, **tune)
                     if mi == 0:   # (a giant row that cannot be staged falls back to a warp per row — by design)
                         assert (info["lanes_per_row"], info["reg_tiles"]) == (g, nt), info
