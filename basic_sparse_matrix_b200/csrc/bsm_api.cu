@@ -376,6 +376,90 @@ struct ScatterTargets {
     uint64_t row_offset = 0;
 };
 
+// ---- launch plan of the vector kernel for one column pass ------------------------------------------------
+// Every default below comes from a same-box A/B sweep kept in profiles/ (tools/sweep.py); bsm_tuning overrides each.
+
+static double mean_row_nnz(const bsm_csr *a) { return a->rows ? (double)a->nnz / (double)a->rows : 0.0; }
+
+// Grouped lanes: fewer lanes per row than the 128-bit loads need -> 2 or 4 register tiles per lane and 32/G rows side
+// by side, every lane group walking its own flat entry stream over a run of consecutive rows (one LDS of the staged A
+// stream then feeds 32/G rows). Exists for full-width 128-bit shapes only. Returns true when `sh` was regrouped;
+// `by_default` says the choice was the heuristic's, not the caller's.
+//   defaults on regular rows (uneven rows stay on the warp-per-row stream, which balances them inside the warp;
+//   3-D Laplacian, profiles/r1_sweep{u,v,w,y,z,aa}_l3d_*.jsonl):
+//     one 128-bit tile per lane, 512-byte rows (x64 f64): 8 lanes x 4 tiles            4.54 -> 3.92 ms
+//     256-byte rows (x32 f64, x64 f32), short rows: 16 -> 8 lanes x 2 tiles            4.28 -> 2.22 ms
+//     128-byte rows (x16 f64), short rows: 8 -> 4 lanes x 2 tiles                      2.70 -> 1.37 ms
+//   (the row-by-row walk of narrow shapes drains its gather window at every row end; rows of ~65 entries, the band
+//   matrix x32 f32, are still faster row by row: 0.45 vs 0.72 ms)
+static bool regroup_lanes(const bsm_csr *a, const bsm_tuning &tn, uint32_t n, size_t s, bool allowed, Shape &sh, bool &by_default)
+{
+    const double mean = mean_row_nnz(a);
+    int want_g = tn.lanes_per_row;
+    by_default = false;
+    if (want_g == 0 && sh.NT == 1 && tn.reg_flavour <= 0 && tn.warps_per_cta <= 0 && tn.prefer_wide_rows == 0 &&
+        (double)a->max_row_nnz <= 4.0 * mean + 8.0) {
+        if (sh.G == 32) want_g = 8;
+        else if ((sh.G == 16 || sh.G == 8) && mean <= 32.0) want_g = sh.G / 2;
+        by_default = want_g > 0;
+    }
+    if (!allowed || want_g <= 0 || want_g >= sh.G || sh.V * (int)s != 16 || n != (uint32_t)(sh.V * sh.G * sh.NT)) return false;
+    const int nt = (int)(n / (uint32_t)(sh.V * want_g));
+    if (!(want_g == 16 || want_g == 8 || want_g == 4) || !(nt == 2 || nt == 4) || n != (uint32_t)(sh.V * want_g * nt)) return false;
+    sh.G = want_g;
+    sh.NT = nt;
+    return true;
+}
+
+// Register-budget flavour (index into the table of spmm_rows_inst.cuh; bsm_tuning.reg_flavour is this + 1).
+//   full-width G == 32: several tiles per lane -> 3 CTAs x 8 warps per SM (4); one tile per lane -> one CTA of 24 warps,
+//   window of 10 gathers (7); scalar A-stream reads in both (LDS.128 reads measured 5-8 % slower);
+//   grouped lanes: one CTA of 24 warps (6) for >= 8 lanes by default, else 3 x 8 warps (4);
+//   narrow one-tile shapes: 0, or 4 = scalar A-stream reads (the default for a row per lane);
+//   the scatter variant exists for the default flavours only.
+static int pick_row_flavour(const bsm_tuning &tn, const Shape &sh, bool wide_full, bool grouped, bool grouped_by_default, bool multi)
+{
+    const bool user_nw = tn.warps_per_cta > 0;
+    int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 8) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 7) : (sh.G == 1 ? 4 : 0));
+    if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;
+    if (grouped) flavour = (tn.reg_flavour == 7 || tn.reg_flavour == 8 || (grouped_by_default && tn.reg_flavour <= 0 && sh.G >= 8)) ? 6 : 4;
+    if (flavour == 3) flavour = 2;                       // retired flavour
+    if (flavour == 7 && sh.NT >= 2) flavour = 4;         // the deep window exists for one tile per lane only
+    if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;
+    return flavour;
+}
+
+// Rows per warp inside a super-batch: the dominant row stride of a stencil-like matrix (so the warps of a CTA sweep
+// adjacent grid lines), else one slice (a few slices for narrow shapes on large matrices: measured on band x 32).
+static uint32_t pick_rows_per_warp(const bsm_csr *a, const bsm_tuning &tn, const Shape &sh, uint32_t R, int nw, int resident)
+{
+    uint32_t P = R;
+    if (tn.rows_per_warp <= 0 && sh.G < 32 && a->rows / ((uint64_t)nw * 4 * R) >= 4ull * g_rt.sm_count) P = 4 * R;
+    if (tn.rows_per_warp > 0) {
+        P = (uint32_t)tn.rows_per_warp;
+    } else if (a->row_stride >= 2 * R) {
+        // P = stride / m keeps warps w and w+m on adjacent lines. Among stride, stride/2, stride/4, ... pick the one that
+        // wastes least to wave quantisation (rounds x rows per warp per round); a larger P wins unless a smaller one
+        // saves more than 10 % (measured on 1/8 and 1/4 row blocks: profiles/r1_sweepk_l3d_n128_s8.jsonl — locality
+        // beats balance). Too few rows for even one round per SM: plain slices.
+        const uint64_t grid_est = (uint64_t)g_rt.sm_count * resident;
+        double best_cost = 0.0;
+        uint32_t best_p = 0;
+        for (uint32_t cand = a->row_stride; cand >= 2 * R; cand /= 2) {
+            const uint64_t supers = (a->rows + (uint64_t)nw * cand - 1) / ((uint64_t)nw * cand);
+            const double cost = (double)((supers + grid_est - 1) / grid_est) * cand;
+            if (best_p == 0 || cost < 0.90 * best_cost) {
+                best_cost = cost;
+                best_p = cand;
+            }
+            if (cand % 2) break;
+        }
+        P = best_p ? best_p : R;
+        if (a->rows / ((uint64_t)nw * P) < (uint64_t)g_rt.sm_count) P = R;
+    }
+    return std::max(R, (P + R - 1) / R * R);
+}
+
 static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags,
                        const ScatterTargets *scatter = nullptr)
 {
@@ -385,174 +469,105 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
     uint32_t tile = tn.col_tile > 0 ? (uint32_t)tn.col_tile : n_total;
     tile = std::min<uint32_t>(tile, 32u * vmax * 4u);   // widest shape one pass can hold in registers
     if (tile < n_total && tile % vmax) tile = std::max<uint32_t>(vmax, tile / vmax * vmax);
-    const double mean = a->rows ? (double)a->nnz / (double)a->rows : 0.0;
+    const double mean = mean_row_nnz(a);
+    const bool multi = scatter && scatter->n_peers > 0;
+    const bool user_R = tn.rows_per_slice > 0, user_nw = tn.warps_per_cta > 0, user_stages = tn.stages > 0;
+    const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
     int passes = 0;
     g_info = bsm_launch_info();
     g_info.algo = BSM_ALGO_VECTOR;
     g_info.col_tile = (int)tile;
     for (uint32_t col0 = 0; col0 < n_total; col0 += tile, ++passes) {
         const uint32_t n = std::min(tile, n_total - col0);
-        const char *bp = (const char *)b->data + (size_t)col0 * s;
         const size_t c_off = ((scatter ? (size_t)scatter->row_offset * c->ld : 0) + (size_t)col0) * s;
-        char *cp = (char *)c->data + c_off;
-        for (bool allow_grouped = true;;) {
+        RowParams p{};
+        p.row_ptr = a->row_ptr;
+        p.col_idx = a->col_idx;
+        p.vals = a->vals;
+        p.B = (const char *)b->data + (size_t)col0 * s;
+        p.C = (char *)c->data + c_off;
+        p.rows = (uint32_t)a->rows;
+        p.n = n;
+        p.ldb = (uint32_t)b->ld;
+        p.ldc = (uint32_t)c->ld;
+        p.flags = flags;
+        if (multi) {
+            p.n_peers = (uint32_t)scatter->n_peers;
+            for (int d = 0; d < scatter->n_peers; ++d) p.peers[d] = (char *)scatter->peer_data[d] + c_off;
+        }
+        // second attempt = without grouped lanes, when their (always staged) slices do not fit shared memory
+        for (bool allow_grouped = true;; allow_grouped = false) {
             Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows != 0);
-            // fewer lanes per row than the 128-bit loads need: 2 or 4 register tiles per lane, 32/G rows side by side
-            // (grouped flat streams; exists for full 128-bit shapes only)
-            bool grouped = false, auto_grouped = false;
-            int want_g = tn.lanes_per_row;
-            // defaults on regular rows (uneven rows stay on the warp-per-row stream, which balances them inside the
-            // warp; same-box A/B on the 3-D Laplacian, profiles/r1_sweep{u,v,w,y,z}_l3d_*.jsonl):
-            //   one 128-bit tile per lane, 512-byte rows (x64 f64): 8 lanes x 4 tiles            4.54 -> 3.92 ms
-            //   256-byte rows (x32 f64, x64 f32), short rows: 16 -> 8 lanes x 2 tiles            4.28 -> 2.22 ms
-            //   128-byte rows (x16 f64), short rows: 8 -> 4 lanes x 2 tiles                      2.70 -> 1.37 ms
-            // (the row-by-row walk of narrow shapes drains its gather window at every row end; rows of ~65 entries,
-            // the band matrix x32 f32, are still faster row by row: 0.45 vs 0.72 ms)
-            if (want_g == 0 && sh.NT == 1 && tn.reg_flavour <= 0 && tn.warps_per_cta <= 0 && tn.prefer_wide_rows == 0 &&
-                (double)a->max_row_nnz <= 4.0 * mean + 8.0) {
-                if (sh.G == 32) want_g = 8;
-                else if ((sh.G == 16 || sh.G == 8) && mean <= 32.0) want_g = sh.G / 2;
-                auto_grouped = want_g > 0;
-            }
-            if (allow_grouped && want_g > 0 && want_g < sh.G && !scatter && sh.V * (int)s == 16 && n == (uint32_t)(sh.V * sh.G * sh.NT)) {
-                const int g = want_g, nt = (int)(n / (uint32_t)(sh.V * g));
-                if ((g == 16 || g == 8 || g == 4) && (nt == 2 || nt == 4) && n == (uint32_t)(sh.V * g * nt)) {
-                    sh.G = g;
-                    sh.NT = nt;
-                    grouped = true;
-                }
-            }
-            const uint32_t rpp = 32u / (uint32_t)sh.G;                 // rows side by side in one warp
-            const uint32_t rq = std::max(4u, rpp);                     // slice granularity (rpp is a power of two)
-            int nw = tn.warps_per_cta > 0 ? std::min(tn.warps_per_cta, 24) : 16;
-            // small matrices: do not leave SMs idle behind a handful of fat super-batches
-            while (tn.warps_per_cta <= 0 && nw > 2 && (uint64_t)nw * rq * (uint64_t)g_rt.sm_count > a->rows) nw /= 2;
-            RowParams p{};
-            p.row_ptr = a->row_ptr;
-            p.col_idx = a->col_idx;
-            p.vals = a->vals;
-            p.B = bp;
-            p.C = cp;
-            p.rows = (uint32_t)a->rows;
-            p.n = n;
-            p.ldb = (uint32_t)b->ld;
-            p.ldc = (uint32_t)c->ld;
-            const bool multi = scatter && scatter->n_peers > 0;
-            if (multi) {
-                p.n_peers = (uint32_t)scatter->n_peers;
-                for (int d = 0; d < scatter->n_peers; ++d) p.peers[d] = (char *)scatter->peer_data[d] + c_off;
-            }
-            // rows per TMA slice: ~128 entries per bulk copy; narrow shapes (32/G rows side by side) want
-            // several passes per slice to amortise the per-slice bookkeeping
-            const bool user_R = tn.rows_per_slice > 0, user_nw = tn.warps_per_cta > 0;
+            bool grouped_by_default = false;
+            const bool grouped = regroup_lanes(a, tn, n, s, allow_grouped && !scatter, sh, grouped_by_default);
+            const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
+            const uint32_t rpp = 32u / (uint32_t)sh.G;   // rows side by side in one warp
+            const uint32_t rq = std::max(4u, rpp);       // slice granularity (rpp is a power of two)
+
+            // rows per TMA slice: ~128 entries per bulk copy (~224 with one register tile per lane, r1_sweepi_*, and for
+            // 8 lanes x 2 tiles); narrow shapes want several row passes per slice to amortise the slice bookkeeping
             uint32_t R;
             if (user_R) {
                 R = (uint32_t)tn.rows_per_slice;
             } else {
-                // measured (profiles/r1_sweepi_*): one register tile per lane (NT = 1) likes ~224-entry slices
-                // (grouped defaults: 8 x 4 tiles measured best at 16 rows x 2 stages, 8 x 2 tiles at 32 rows x 2 stages)
-                const double target = ((sh.G == 32 && sh.NT == 1) || (grouped && auto_grouped && sh.NT == 2)) ? 224.0 : 128.0;
+                const double target = ((sh.G == 32 && sh.NT == 1) || (grouped && grouped_by_default && sh.NT == 2)) ? 224.0 : 128.0;
                 R = (uint32_t)std::min<double>(256.0, std::max(1.0, target / std::max(1.0, mean)));
                 if (sh.G < 32) R = std::max(R, 4u * rpp);
             }
             R = std::max(rq, R / rq * rq);
-            // register-budget flavour (spmm_rows_inst.cuh); flavours 2 and 3 exist for full-width G == 32 shapes
-            const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
-            // defaults for full-width shapes, from the same-box A/B sweeps in profiles/: several register tiles per
-            // lane -> 3 CTAs x 8 warps per SM; one tile per lane -> one CTA of 24 warps (24 adjacent lines share
-            // L1); scalar A-stream reads in both (LDS.128 reads measured 5-8 % slower)
-            int flavour = tn.reg_flavour > 0 ? std::min(tn.reg_flavour, 8) - 1 : (wide_full && !user_nw ? (sh.NT >= 2 ? 4 : 7) : (sh.G == 1 ? 4 : 0));   // a row per lane (G = 1): scalar reads too
-            if (!wide_full && !(sh.G < 32 && flavour == 4)) flavour = 0;   // narrow shapes: default, or 4 = scalar A-stream reads
-            if (grouped) {
-                flavour = (tn.reg_flavour == 7 || tn.reg_flavour == 8 || (auto_grouped && tn.reg_flavour <= 0 && sh.G >= 8)) ? 6 : 4;
-            }   // one CTA of 24 warps, or 3 x 8 warps (default)
-            if (flavour == 3) flavour = 2;   // retired flavour
-            if (flavour == 7 && sh.NT >= 2) flavour = 4;   // the deep window exists for one tile per lane only
-            if (multi) flavour = wide_full ? (sh.NT >= 2 ? 4 : 2) : 0;       // the scatter variant exists for the default flavours
-            // threads per CTA each flavour was compiled for (spmm_rows_inst.cuh)
-            const bool big_cta = (wide_full && (flavour == 5 || flavour == 6 || flavour == 7)) || (grouped && flavour == 6);   // one CTA of 24 warps per SM
+
+            int flavour = pick_row_flavour(tn, sh, wide_full, grouped, grouped_by_default, multi);
+            // warps per CTA: what the flavour was compiled for; fewer on small matrices, so that no SM idles behind a
+            // handful of fat super-batches
+            const bool big_cta = (wide_full && (flavour == 5 || flavour == 6 || flavour == 7)) || (grouped && flavour == 6);
             const int max_warps = big_cta ? 24 : ((flavour >= 2 && (wide_full || grouped)) ? 8 : 16);
-            if (big_cta && !user_nw) {
-                nw = 24;
-                // few rows: smaller CTAs, so that every SM still gets a super-batch
-                while (nw > 3 && (uint64_t)nw * R * (uint64_t)g_rt.sm_count > a->rows) nw /= 2;
+            int nw = user_nw ? std::min(tn.warps_per_cta, 24) : (big_cta ? 24 : 16);
+            if (!user_nw) {
+                const uint64_t rows_per_warp_min = big_cta ? R : rq;
+                const int nw_floor = big_cta ? 3 : 2;
+                while (nw > nw_floor && (uint64_t)nw * rows_per_warp_min * (uint64_t)g_rt.sm_count > a->rows) nw /= 2;
             }
             nw = std::min(nw, max_warps);
-            p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : (grouped && auto_grouped && sh.G >= 8 ? 2u : 3u);
-            p.flags = flags;
-            // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start).
-            // Shrink, in this order, the ring depth, the slice and the CTA until the rings fit: first under
-            // a soft limit that leaves most of the 228 KB to L1 (where wide B rows live), then under the
-            // hardware limit. If even the smallest slice cannot be staged, col_idx / values are read from
-            // global memory instead (unstaged variant).
-            const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
+
+            // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start, + slack: the
+            // vectorised A-stream reads run up to two gather windows past the slice). Shrink, in this order, the ring
+            // depth, the slice and the CTA until the rings fit: first under a soft limit that leaves most of the 228 KB
+            // to L1 (where wide B rows live), then under the hardware limit. If even the smallest slice cannot be
+            // staged, col_idx / values are read from global memory instead (unstaged variant).
             const int resident = ((wide_full || grouped) && (flavour == 2 || flavour == 4)) ? 3 : 1;   // CTAs per SM the flavour targets
             const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (160 * 1024) / resident);
-            const uint32_t window = (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight (U)
-            const uint32_t window_f7 = 10u;
+            const uint32_t window = flavour == 7 ? 10u : (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight
+            const uint32_t r_floor = sh.G < 32 ? std::max(rq, 2u * rpp) : rq;
             p.R = R;
+            p.stages = user_stages ? (uint32_t)std::min(tn.stages, 8) : (grouped && grouped_by_default && sh.G >= 8 ? 2u : 3u);
             auto smem_now = [&]() {
-                // + slack: the vectorised A-stream reads of the kernel run up to two gather windows past the slice
-                p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 2 * (flavour == 7 ? window_f7 : window) + 4;
+                p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 2 * window + 4;
                 return row_kernel_smem_bytes(a->dtype, p, nw);
             };
-            const uint32_t r_floor = sh.G < 32 ? std::max(rq, 2u * rpp) : rq;
             size_t smem = smem_now();
-            const bool user_stages = tn.stages > 0;
             while (smem > smem_soft && p.stages > 2 && !user_stages) { --p.stages; smem = smem_now(); }
             while (smem > smem_soft && p.R > r_floor && !user_R) { p.R = std::max(r_floor, p.R / 2 / rq * rq); smem = smem_now(); }
             while (smem > smem_soft && nw > 8 && !user_nw) { nw /= 2; smem = smem_now(); }
             while (smem > smem_max && p.stages > 1) { --p.stages; smem = smem_now(); }
             while (smem > smem_max && p.R > rq && !user_R) { p.R = std::max(rq, p.R / 2 / rq * rq); smem = smem_now(); }
             while (smem > smem_max && nw > 2 && !user_nw) { nw /= 2; smem = smem_now(); }
-            if (smem > smem_max && grouped) {   // the grouped shapes have no unstaged variant: a warp per row instead
-                allow_grouped = false;
-                continue;
-            }
-            if (smem > smem_max) {   // rows too long to stage: unstaged variant (row_ptr windows only)
+            if (smem > smem_max && grouped) continue;   // the grouped shapes have no unstaged variant: a warp per row instead
+            if (smem > smem_max) {                      // rows too long to stage: unstaged variant (row_ptr windows only)
                 flavour = -1;
                 p.cap = 0;
-                p.stages = tn.stages > 0 ? (uint32_t)std::min(tn.stages, 8) : 3u;
+                p.stages = user_stages ? (uint32_t)std::min(tn.stages, 8) : 3u;
                 smem = row_kernel_smem_bytes(a->dtype, p, nw);
             }
             if (smem > smem_max) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: slice ring does not fit shared memory");
-            R = p.R;
-            // rows per warp inside a super-batch: the dominant row stride of a stencil-like matrix (so the
-            // warps of a CTA sweep adjacent lines), else one slice
-            uint32_t P = R;
-            if (tn.rows_per_warp <= 0 && sh.G < 32 && a->rows / ((uint64_t)nw * 4 * R) >= 4ull * g_rt.sm_count) P = 4 * R;   // measured: band x 32
-            if (tn.rows_per_warp > 0) {
-                P = (uint32_t)tn.rows_per_warp;
-            } else if (a->row_stride >= 2 * R) {
-                // P = stride / m keeps warps w and w+m on adjacent lines. Among stride, stride/2, stride/4, ...
-                // pick the one that wastes least to wave quantisation (rounds x rows per warp per round); a
-                // larger P wins unless a smaller one saves more than 10 % (measured on 1/8 and 1/4 row blocks:
-                // profiles/r1_sweepk_l3d_n128_s8.jsonl — locality beats balance). Too few rows for even one
-                // round per SM: fall back to plain slices.
-                const uint64_t grid_est = (uint64_t)g_rt.sm_count * resident;
-                double best_cost = 0.0;
-                uint32_t best_p = 0;
-                for (uint32_t cand = a->row_stride; cand >= 2 * R; cand /= 2) {
-                    const uint64_t supers = (a->rows + (uint64_t)nw * cand - 1) / ((uint64_t)nw * cand);
-                    const double cost = (double)((supers + grid_est - 1) / grid_est) * cand;
-                    if (best_p == 0 || cost < 0.90 * best_cost) {
-                        best_cost = cost;
-                        best_p = cand;
-                    }
-                    if (cand % 2) break;
-                }
-                P = best_p ? best_p : R;
-                if (a->rows / ((uint64_t)nw * P) < (uint64_t)g_rt.sm_count) P = R;
-            }
-            P = std::max(R, (P + R - 1) / R * R);
-            p.P = P;
-            const uint64_t S = (uint64_t)nw * P;
+
+            p.P = pick_rows_per_warp(a, tn, sh, p.R, nw, resident);
+            const uint64_t S = (uint64_t)nw * p.P;
             p.num_super = (uint32_t)((a->rows + S - 1) / S);
             const int block = nw * 32;
             int occ = 0;
             BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, flavour, multi, block, smem, &occ));
             if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_vector: kernel does not fit on an SM");
-            int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
+            const int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
             const int grid = (int)std::min<uint64_t>(p.num_super, (uint64_t)g_rt.sm_count * ctas);
             if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, flavour, multi, grid, block, smem, ctas, g_rt.stream));
             g_info.kernels += grid > 0;
