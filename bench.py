@@ -59,6 +59,9 @@ WORKLOADS = {
     "laplace3d_256_n32_f64": ("laplace3d", dict(g=256), 32, "f64"),
     "laplace3d_256_n64_f32": ("laplace3d", dict(g=256), 64, "f32"),
     "laplace3d_256_n16_f64": ("laplace3d", dict(g=256), 16, "f64"),
+    # uniformly random columns, Poisson(8) rows: regular row lengths without any locality in B
+    "uniform22_n64_f64": ("rmat", dict(scale=22, edges=8 << 22, a=0.25, b=0.25, c=0.25), 64, "f64"),
+    "uniform22_n32_f64": ("rmat", dict(scale=22, edges=8 << 22, a=0.25, b=0.25, c=0.25), 32, "f64"),
 }
 DEFAULT_WORKLOAD = "laplace3d_256_n128_f64"
 NP_DTYPE = {"f64": np.float64, "f32": np.float32}
@@ -165,7 +168,8 @@ def make_device_csr(gpu, kind, prm, dtype, r0=0, r1=None):
         return gpu.DeviceCsr.band(prm["n"], prm["hb"], r0, r1, dtype)
     if kind == "rmat":
         from basic_sparse_matrix_b200 import gen
-        return gpu.DeviceCsr.rmat(prm["scale"], prm["edges"], seed=3, mode=gen.MODE_EXACT, dtype=dtype)
+        return gpu.DeviceCsr.rmat(prm["scale"], prm["edges"], a=prm.get("a", 0.57), b=prm.get("b", 0.19), c=prm.get("c", 0.19),
+                                  seed=3, mode=gen.MODE_EXACT, dtype=dtype)
     raise ValueError(kind)
 
 

@@ -42,3 +42,27 @@ def test_python_binding_covers_every_symbol():
     for n in declared_functions():
         assert getattr(L, n).argtypes is not None or n in ("bsm_abi_version", "bsm_sync", "bsm_last_error_string",
                                                            "bsm_kernel_launch_count", "bsm_l2_flush"), n
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """bsm_tuning / bsm_launch_info are passed by pointer: the ctypes mirrors must have the header's
+    size and field offsets (checked by compiling a probe against include/bsm.h)."""
+    import subprocess
+    fields_t = [k for k, _ in _lib.Tuning._fields_]
+    fields_i = [k for k, _ in _lib.LaunchInfo._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "bsm.h"', 'int main(void) {',
+           'printf("T %zu\\n", sizeof(bsm_tuning)); printf("I %zu\\n", sizeof(bsm_launch_info));']
+    src += [f'printf("T.{k} %zu\\n", offsetof(bsm_tuning, {k}));' for k in fields_t]
+    src += [f'printf("I.{k} %zu\\n", offsetof(bsm_launch_info, {k}));' for k in fields_i]
+    src += ['return 0; }']
+    c = tmp_path / "probe.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(got["T"]) == ctypes.sizeof(_lib.Tuning)
+    assert int(got["I"]) == ctypes.sizeof(_lib.LaunchInfo)
+    for k in fields_t:
+        assert int(got[f"T.{k}"]) == getattr(_lib.Tuning, k).offset, k
+    for k in fields_i:
+        assert int(got[f"I.{k}"]) == getattr(_lib.LaunchInfo, k).offset, k
