@@ -17,6 +17,9 @@
  *   - all work is enqueued on one CUDA stream per process (bsm_set_stream can adopt an
  *     external one, e.g. a torch stream, passed as an opaque pointer); functions that return
  *     host data synchronise that stream before returning;
+ *   - threading: one process drives one GPU (bsm_init) from one host thread at a time, like the
+ *     single-threaded reference; error strings and bsm_last_launch_info are per thread, the device,
+ *     stream and allocator state are per process and NOT locked — serialise calls from several threads;
  *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails
  *     with BSM_ERR_NO_DEVICE / BSM_ERR_CUDA.
  */
