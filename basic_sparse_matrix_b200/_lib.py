@@ -30,8 +30,8 @@ BSM_ERR_NO_DEVICE = 9
 BSM_ERR_NOT_SUPPORTED = 10
 
 BSM_F32, BSM_F64 = 0, 1
-ALGO_AUTO, ALGO_VECTOR, ALGO_MERGE = 0, 1, 2
-ALGO_NAMES = {"auto": ALGO_AUTO, "vector": ALGO_VECTOR, "merge": ALGO_MERGE}
+ALGO_AUTO, ALGO_VECTOR, ALGO_MERGE, ALGO_ROWBLOCK = 0, 1, 2, 3
+ALGO_NAMES = {"auto": ALGO_AUTO, "vector": ALGO_VECTOR, "merge": ALGO_MERGE, "rowblock": ALGO_ROWBLOCK}
 
 TUNE_A_EVICT_FIRST = 0x1
 TUNE_C_STREAMING = 0x2

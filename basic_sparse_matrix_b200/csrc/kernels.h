@@ -62,6 +62,23 @@ int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size
                       int *grid_out);
 int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream, int *launched);
 
+// ---- row-block kernel for band-like matrices (spmm_rowblock.cu) --------------------------------------
+constexpr uint32_t kRowBlockRows = 8;   // consecutive rows one lane group accumulates side by side
+struct RowBlockParams {
+    const uint32_t *row_ptr;
+    const uint32_t *col_idx;
+    const void *vals;
+    const void *B;   // already offset to the first column of this pass
+    void *C;         // likewise
+    uint32_t rows, n, ldb, ldc, flags;
+    uint32_t cap;    // staged values per warp (set by the launcher)
+};
+// out[0] += sum over blocks of kRowBlockRows rows of the length of the union of their column ranges,
+// out[1] += blocks holding a row whose stored columns are not a run of consecutive indices
+int launch_rowblock_probe(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, unsigned long long *out, cudaStream_t stream);
+int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
+                         int *grid_out, int *block_out, int *smem_out);
+
 // ---- format conversion / construction (convert.cu) ---------------------------------------------
 int launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t count, uint64_t bound, uint64_t subtract,
                       uint32_t *flag /* set to 1 when (v - subtract) >= bound */, cudaStream_t stream);

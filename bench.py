@@ -247,7 +247,7 @@ def run_config1(torch, gpu, peak, e=900_000):
     for h in (A, B, C):
         h.close()
     return {"workload": f"bench_as_written_e{e}_n10_f64", "rows": 1000, "nnz": nnz, "n": 10, "dtype": "f64",
-            "algo": "merge" if info["algo"] == 2 else "vector", "ms_per_step": round(total_ms / 20, 4), "ms_best": round(min(per), 4),
+            "algo": {2: "merge", 3: "rowblock"}.get(info["algo"], "vector"), "ms_per_step": round(total_ms / 20, 4), "ms_best": round(min(per), 4),
             "gflops": round(2.0 * nnz * 10 / (total_ms / 20 * 1e-3) / 1e9, 2), "kernels_per_step": info["kernels"],
             "host_call_ms": round(t_host * 1e3, 3), "host_call_gflops": round(2.0 * nnz * 10 / t_host / 1e9, 3),
             "cpu_port_ms_full": round(t_cpu * 1e3, 3), "cpu_port_gflops": round(2.0 * nnz * 10 / t_cpu / 1e9, 4),
@@ -270,7 +270,7 @@ def run_extra(torch, gpu, name, steps, warmup, peak):
     t = total_ms / steps * 1e-3
     bm = bytes_min(ai["rows"], ai["nnz"], ai["cols"], n, s)
     out = {"workload": name, "rows": ai["rows"], "nnz": ai["nnz"], "n": n, "dtype": dt,
-           "algo": "merge" if info["algo"] == 2 else "vector", "ms_per_step": round(total_ms / steps, 4),
+           "algo": {2: "merge", 3: "rowblock"}.get(info["algo"], "vector"), "ms_per_step": round(total_ms / steps, 4),
            "ms_best": round(min(per), 4), "gflops": round(2.0 * ai["nnz"] * n / t / 1e9, 1),
            "eff_gbs": round(bm / t / 1e9, 1), "roofline_frac": round(bm / t / 1e9 / peak, 4),
            "kernels_per_step": info["kernels"]}

@@ -60,7 +60,14 @@ typedef enum bsm_status {
 typedef enum bsm_dtype { BSM_F32 = 0, BSM_F64 = 1 } bsm_dtype;
 
 /* kernel family (north_star): warp-per-row vector CSR, or nnz-balanced merge-path */
-typedef enum bsm_algo { BSM_ALGO_AUTO = 0, BSM_ALGO_VECTOR = 1, BSM_ALGO_MERGE = 2 } bsm_algo;
+typedef enum bsm_algo {
+    BSM_ALGO_AUTO = 0,
+    BSM_ALGO_VECTOR = 1,   /* row-parallel vector CSR: stored order, unfused -> bit-identical to the reference */
+    BSM_ALGO_MERGE = 2,    /* nnz-balanced merge path (power-law rows)                                     */
+    BSM_ALGO_ROWBLOCK = 3  /* vector CSR for band-like matrices (every row a run of consecutive columns): blocks of
+                              consecutive rows share their B-row loads; same order and rounding as BSM_ALGO_VECTOR;
+                              BSM_ERR_NOT_SUPPORTED when the matrix has a row that is not such a run           */
+} bsm_algo;
 
 /* bsm_tuning.flags */
 #define BSM_TUNE_A_EVICT_FIRST 0x1u   /* L2 evict-first policy on the TMA bulk copies of col_idx/values */
@@ -97,7 +104,7 @@ typedef struct bsm_tuning {
 
 /* what the last bsm_spmm* call on this thread actually launched */
 typedef struct bsm_launch_info {
-    int32_t algo;            /* BSM_ALGO_VECTOR or BSM_ALGO_MERGE                                   */
+    int32_t algo;            /* BSM_ALGO_VECTOR, BSM_ALGO_MERGE or BSM_ALGO_ROWBLOCK                */
     int32_t kernels;         /* kernels launched by the call                                        */
     int32_t vec_elems;       /* elements per lane per load (V)                                      */
     int32_t lanes_per_row;   /* G                                                                   */

@@ -191,6 +191,54 @@ def test_vector_slow_path_rows_longer_than_a_stage(gpu):
     assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), "slow path")
 
 
+# ---- row-block kernel (band-like matrices) -----------------------------------------------------------------
+def _runs_csr(rng, m, k, dtype, max_len, empty_frac=0.1, band=True):
+    """Every row stores one run of consecutive columns (a band when band=True, else runs anywhere)."""
+    vals, cols, ri = [], [], [0]
+    for r in range(m):
+        if rng.random() >= empty_frac:
+            ln = int(rng.integers(1, max_len + 1))
+            lo = max(0, min(k - ln, (r * k // m) - ln // 2)) if band else int(rng.integers(0, k - ln + 1))
+            ln = min(ln, k - lo)
+            cols += list(range(lo, lo + ln))
+            vals += rng.standard_normal(ln).tolist()
+        ri.append(len(cols))
+    return np.array(vals, dtype), np.array(cols, np.uint64), np.array(ri, np.uint64)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rowblock_bitwise(gpu, dtype):
+    """BSM_ALGO_ROWBLOCK: blocks of 8 consecutive rows share their B-row loads; every row still sums in stored
+    order with the unfused multiply-add -> bit-exact for any values (ragged bands, empty rows, runs anywhere)."""
+    rng = np.random.default_rng(606)
+    for m, k, max_len, band in ((1003, 1003, 40, True), (77, 300, 65, True), (5, 9, 9, True), (1, 4, 3, True), (400, 5000, 30, False)):
+        v, ci, ri = _runs_csr(rng, m, k, dtype, max_len, band=band)
+        for n in (1, 3, 8, 32, 33, 64, 100, 130):
+            b = random_dense(rng, k, n, dtype)
+            got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "rowblock")
+            assert info["algo"] == _lib.ALGO_ROWBLOCK
+            assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), f"rowblock m={m} n={n} band={band}")
+        got, _ = gpu_product(gpu, (m, k), v, ci, ri, random_dense(np.random.default_rng(1), k, 64, dtype), "rowblock", col_tile=16)
+        assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, random_dense(np.random.default_rng(1), k, 64, dtype)), "rowblock col_tile")
+
+
+def test_rowblock_refuses_rows_that_are_not_runs_and_auto_picks_it_for_bands(gpu):
+    rng = np.random.default_rng(607)
+    v, ci, ri = random_csr(rng, 300, 300, np.float64, mean_len=6)
+    with pytest.raises(_lib.BsmError):
+        gpu_product(gpu, (300, 300), v, ci, ri, random_dense(rng, 300, 8, np.float64), "rowblock")
+    # a band large enough for the heuristic: AUTO runs the row-block kernel, bit-identical to the vector kernel
+    a = gpu.DeviceCsr.band(40_000, 16, dtype=np.float32)
+    bd = gpu.DeviceDense.generate(40_000, 32, seed=9, mode=gen.MODE_REAL, dtype=np.float32)
+    auto = a.mul_dense(bd)
+    assert gpu.last_launch_info()["algo"] == _lib.ALGO_ROWBLOCK
+    vec = a.mul_dense(bd, algo="vector")
+    assert gpu.last_launch_info()["algo"] == _lib.ALGO_VECTOR
+    assert_bitwise(auto.to_rowmajor(), vec.to_rowmajor(), "rowblock vs vector on a band")
+    for h in (a, bd, auto, vec):
+        h.close()
+
+
 # ---- merge-path kernel -------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", NS)

@@ -68,7 +68,7 @@ def main():
     with torch.cuda.stream(stream):
         for pt in args.points.split(";"):
             kw = {k: int(v, 0) for k, v in (kv.split("=") for kv in pt.split(",") if kv)}
-            tuning = gpu.make_tuning(args.algo, **kw)
+            tuning = gpu.make_tuning(kw.pop("algo", args.algo), **kw)
             try:
                 total_ms, per = bench.time_device_steps(torch, A, B, C, args.steps, args.warmup, tuning)
             except Exception as ex:
