@@ -768,7 +768,10 @@ static int spmm_rowblock(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, con
         p.ldc = (uint32_t)c->ld;
         p.flags = flags;
         int grid = 0, block = 0, smem = 0;
-        BSM_TRY(launch_spmm_rowblock(a->dtype, sh, p, a->max_row_nnz, g_rt.sm_count, (size_t)g_rt.max_smem_optin - 1024, g_rt.stream, &grid, &block, &smem));
+        // rows one lane group accumulates side by side: 8 when a warp holds one block (G = 32), 4 when it holds several
+        // (more warps fit; band x32 f32 0.328 -> 0.296 ms, x128 f32 1.26 -> 1.15 ms the other way: r1_sweepag_band_*)
+        const int rb = tn.rows_per_slice == 4 || tn.rows_per_slice == 8 ? tn.rows_per_slice : (sh.G == 32 ? 8 : 4);
+        BSM_TRY(launch_spmm_rowblock(a->dtype, sh, p, rb, a->max_row_nnz, g_rt.sm_count, (size_t)g_rt.max_smem_optin - 1024, g_rt.stream, &grid, &block, &smem));
         g_info.smem_bytes = smem;
         g_info.kernels += grid > 0;
         g_info.vec_elems = sh.V;
@@ -776,7 +779,7 @@ static int spmm_rowblock(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, con
         g_info.reg_tiles = sh.NT;
         g_info.grid = grid;
         g_info.block = block;
-        g_info.rows_per_slice = (int)kRowBlockRows;
+        g_info.rows_per_slice = rb;
     }
     g_info.passes = passes;
     return BSM_OK;
@@ -809,7 +812,7 @@ static int choose_algo(const bsm_csr *a_const, uint64_t n_cols, int requested, i
     // (output rows of at least 64 bytes: with fewer lanes per row the blocks' value reads are too scattered — SpMV on the
     // band measured 0.50 vs 0.11 ms)
     if (mean >= 16.0 && (double)a->max_row_nnz <= 4.0 * mean + 8.0 && a->rows >= (uint64_t)g_rt.sm_count * 64 &&
-        n_cols * dtype_size(a->dtype) >= 64 && 64 * a->max_row_nnz * dtype_size(a->dtype) <= 24 * 1024) {   // (and a warp block's values fit its stage)
+        n_cols * dtype_size(a->dtype) >= 64) {
         BSM_TRY(ensure_rowblock_probe(a));
         if (a->rowblock_state == 1 && a->rowblock_union * 2 <= a->nnz) *algo = BSM_ALGO_ROWBLOCK;
     }
@@ -834,7 +837,11 @@ static int spmm_dispatch(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, con
     int algo = BSM_ALGO_VECTOR;
     BSM_TRY(choose_algo(a, b->cols, tn.algo, &algo));
     if (algo == BSM_ALGO_MERGE) return spmm_merge(a, b, c, tn, flags);
-    if (algo == BSM_ALGO_ROWBLOCK) return spmm_rowblock(a, b, c, tn, flags);
+    if (algo == BSM_ALGO_ROWBLOCK) {
+        const int st = spmm_rowblock(a, b, c, tn, flags);
+        // chosen by the heuristic but a warp block's values do not fit shared memory: the plain vector kernel
+        if (st != BSM_ERR_NOT_SUPPORTED || tn.algo == BSM_ALGO_ROWBLOCK) return st;
+    }
     return spmm_vector(a, b, c, tn, flags);
 }
 

@@ -76,7 +76,7 @@ struct RowBlockParams {
 // out[0] += sum over blocks of kRowBlockRows rows of the length of the union of their column ranges,
 // out[1] += blocks holding a row whose stored columns are not a run of consecutive indices
 int launch_rowblock_probe(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, unsigned long long *out, cudaStream_t stream);
-int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
+int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p, int rows_per_block /* 4 or 8 */, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
                          int *grid_out, int *block_out, int *smem_out);
 
 // ---- format conversion / construction (convert.cu) ---------------------------------------------

@@ -44,7 +44,7 @@ __global__ void rowblock_probe_kernel(const uint32_t *__restrict__ row_ptr, cons
 // contiguous piece of the value array: a single TMA bulk copy, cp.async.bulk -> UBLKCP, completing on the warp's
 // mbarrier) + the mbarriers. The value reads are then warp-broadcast LDS instead of scattered global loads.
 template <typename T, int V, int G, int RB, bool FULLN>
-__global__ void __launch_bounds__(256, 2) spmm_rowblock_kernel(const RowBlockParams p)
+__global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(const RowBlockParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int RPP = 32 / G;                  // lane groups (row blocks) per warp
@@ -173,41 +173,45 @@ int launch_rowblock_probe(const uint32_t *row_ptr, const uint32_t *col_idx, uint
     return BSM_OK;
 }
 
-template <typename T, int V, int G> static const void *rowblock_ptr(bool fulln)
+template <typename T, int V, int G> static const void *rowblock_ptr(bool fulln, int rb)
 {
-    return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, kRowBlockRows, true>)
-                 : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, kRowBlockRows, false>);
+    if (rb == 4)
+        return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, true>)
+                     : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, false>);
+    return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 8, true>)
+                 : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 8, false>);
 }
-template <typename T, int V> static const void *rowblock_select_g(int G, bool fulln)
+template <typename T, int V> static const void *rowblock_select_g(int G, bool fulln, int rb)
 {
     switch (G) {
-        case 32: return rowblock_ptr<T, V, 32>(fulln);
-        case 16: return rowblock_ptr<T, V, 16>(fulln);
-        case 8: return rowblock_ptr<T, V, 8>(fulln);
-        case 4: return rowblock_ptr<T, V, 4>(fulln);
-        case 2: return rowblock_ptr<T, V, 2>(fulln);
-        case 1: return rowblock_ptr<T, V, 1>(fulln);
+        case 32: return rowblock_ptr<T, V, 32>(fulln, rb);
+        case 16: return rowblock_ptr<T, V, 16>(fulln, rb);
+        case 8: return rowblock_ptr<T, V, 8>(fulln, rb);
+        case 4: return rowblock_ptr<T, V, 4>(fulln, rb);
+        case 2: return rowblock_ptr<T, V, 2>(fulln, rb);
+        case 1: return rowblock_ptr<T, V, 1>(fulln, rb);
     }
     return nullptr;
 }
 
-int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p_in, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
+int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p_in, int rb, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
                          int *grid_out, int *block_out, int *smem_out)
 {
     if (sh.NT != 1) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rowblock: one register tile per lane only");
     const bool fulln = p_in.n == (uint32_t)(sh.V * sh.G);
     const void *k = nullptr;
     if (dtype == BSM_F64) {
-        if (sh.V == 1) k = rowblock_select_g<double, 1>(sh.G, fulln);
-        if (sh.V == 2) k = rowblock_select_g<double, 2>(sh.G, fulln);
+        if (sh.V == 1) k = rowblock_select_g<double, 1>(sh.G, fulln, rb);
+        if (sh.V == 2) k = rowblock_select_g<double, 2>(sh.G, fulln, rb);
     } else {
-        if (sh.V == 1) k = rowblock_select_g<float, 1>(sh.G, fulln);
-        if (sh.V == 2) k = rowblock_select_g<float, 2>(sh.G, fulln);
-        if (sh.V == 4) k = rowblock_select_g<float, 4>(sh.G, fulln);
+        if (sh.V == 1) k = rowblock_select_g<float, 1>(sh.G, fulln, rb);
+        if (sh.V == 2) k = rowblock_select_g<float, 2>(sh.G, fulln, rb);
+        if (sh.V == 4) k = rowblock_select_g<float, 4>(sh.G, fulln, rb);
     }
     if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rowblock: no kernel for this lane shape");
     RowBlockParams pc = p_in;
-    const uint64_t wr = (uint64_t)(32 / sh.G) * kRowBlockRows;                 // rows per warp block
+    if (rb != 4 && rb != 8) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_rowblock: 4 or 8 rows per block");
+    const uint64_t wr = (uint64_t)(32 / sh.G) * (uint64_t)rb;                  // rows per warp block
     const uint64_t cap = ((wr * max_row_nnz + 3 + 3) & ~3ull) + 4;             // + aligned start, rounded size
     int block = 256;
     auto smem_of = [&](int threads) { return (size_t)(threads / 32) * (cap * dtype_size(dtype) + 8); };

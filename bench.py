@@ -55,6 +55,8 @@ WORKLOADS = {
     "rmat20_n64_f32": ("rmat", dict(scale=20, edges=100 << 20), 64, "f32"),
     "band_1m_hb32_n32_f32": ("band", dict(n=1 << 20, hb=32), 32, "f32"),  # configs[4] GPU side
     "band_1m_hb32_n1_f32": ("band", dict(n=1 << 20, hb=32), 1, "f32"),
+    "band_1m_hb32_n64_f64": ("band", dict(n=1 << 20, hb=32), 64, "f64"),   # sweep-only: wider / f64 products on the band
+    "band_1m_hb32_n128_f32": ("band", dict(n=1 << 20, hb=32), 128, "f32"),
     # sweep-only shapes (tools/sweep.py): 256-byte and 128-byte output rows on the stencil matrix
     "laplace3d_256_n32_f64": ("laplace3d", dict(g=256), 32, "f64"),
     "laplace3d_256_n64_f32": ("laplace3d", dict(g=256), 64, "f32"),
