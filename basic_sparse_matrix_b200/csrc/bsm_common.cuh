@@ -245,6 +245,30 @@ __device__ __forceinline__ float mul_add_unfused(float a, float b, float acc) { 
 __device__ __forceinline__ double mul_add_fused(double a, double b, double acc) { return fma(a, b, acc); }
 __device__ __forceinline__ float mul_add_fused(float a, float b, float acc) { return fmaf(a, b, acc); }
 
+// acc += a * b over a lane's V elements, product and sum rounded separately (as mul_add_unfused). f32 with an even V
+// uses Blackwell's packed multiply: one FMUL2 per two products, then scalar FADDs — 3 instructions per two elements
+// instead of 4. (A packed add after the packed multiply is NOT used: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into one FFMA2, i.e. a fused multiply-add; tests/test_build_flags.py checks the SASS for that.)
+template <typename T, int V> __device__ __forceinline__ void axpy_unfused(T a, const T (&b)[V], T (&acc)[V])
+{
+    if constexpr (sizeof(T) == 4 && V % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < V; i += 2) {
+            unsigned long long aa, bb, pp;
+            float p0, p1;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[i]), "f"(b[i + 1]));
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pp) : "l"(aa), "l"(bb));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(pp));
+            acc[i] = __fadd_rn(acc[i], p0);
+            acc[i + 1] = __fadd_rn(acc[i + 1], p1);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = mul_add_unfused(a, b[i], acc[i]);
+    }
+}
+
 template <bool FUSED, typename T> __device__ __forceinline__ T mul_add(T a, T b, T acc)
 {
     if constexpr (FUSED)

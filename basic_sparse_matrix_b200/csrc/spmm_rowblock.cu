@@ -124,9 +124,7 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
                 for (int r = 0; r < RB; ++r) {
                     const uint32_t off = j - first[r];
                     if (off < len[r]) {   // row r stores column j, at entry base + off; ascending j = stored order
-                        const T a = va[base[r] + off];
-#pragma unroll
-                        for (int i = 0; i < V; ++i) acc[r].x[i] = mul_add<false>(a, b.x[i], acc[r].x[i]);
+                        axpy_unfused<T, V>(va[base[r] + off], b.x, acc[r].x);
                     }
                 }
             }
@@ -147,9 +145,7 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
                     if (col_ok) b.template load<false>(reinterpret_cast<const T *>(brow), 0ull);
 #pragma unroll
                     for (int r = 0; r < RB; ++r) {
-                        const T a = vrow[r][j];
-#pragma unroll
-                        for (int i = 0; i < V; ++i) acc[r].x[i] = mul_add<false>(a, b.x[i], acc[r].x[i]);
+                        axpy_unfused<T, V>(vrow[r][j], b.x, acc[r].x);
                     }
                 }
             }
