@@ -327,7 +327,7 @@ inline void init(int device)
     const int st = bsm_init(device);
     if (st != BSM_OK) detail::throw_status(st);
 }
-enum class Algo { Auto = BSM_ALGO_AUTO, VectorCsr = BSM_ALGO_VECTOR, MergePath = BSM_ALGO_MERGE };
+enum class Algo { Auto = BSM_ALGO_AUTO, VectorCsr = BSM_ALGO_VECTOR, MergePath = BSM_ALGO_MERGE, RowBlock = BSM_ALGO_ROWBLOCK };
 
 template <typename T> class DeviceDense {
     bsm_dense *h_ = nullptr;

@@ -6,7 +6,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
     let nvcc = format!("{cuda}/bin/nvcc");
-    let sources = ["bsm_api.cu", "spmm_rows.cu", "spmm_rows_f64.cu", "spmm_rows_f32.cu", "spmm_merge.cu", "convert.cu", "gen.cu",
+    let sources = ["bsm_api.cu", "spmm_rows.cu", "spmm_rows_f64.cu", "spmm_rows_f32.cu", "spmm_merge.cu", "spmm_rowblock.cu", "convert.cu", "gen.cu",
                    "bsm_nccl.cu"];
     let mut objects = Vec::new();
     for src in sources {

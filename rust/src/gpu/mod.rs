@@ -68,7 +68,7 @@ impl_scalar!(f64, ffi::BSM_F64, bsm_csr_upload_f64, bsm_csr_download_f64, bsm_de
 impl_scalar!(f32, ffi::BSM_F32, bsm_csr_upload_f32, bsm_csr_download_f32, bsm_dense_upload_f32, bsm_dense_download_f32, bsm_mul_vector_f32);
 
 #[derive(Clone, Copy, Debug, PartialEq)]
-pub enum Algo { Auto = 0, VectorCsr = 1, MergePath = 2 }
+pub enum Algo { Auto = 0, VectorCsr = 1, MergePath = 2, RowBlock = 3 }
 
 /// Select the GPU of this process (one process per GPU).
 pub fn init(device: i32) -> Result<(), GpuError> { check(unsafe { ffi::bsm_init(device) }) }
