@@ -35,7 +35,6 @@ ALGO_NAMES = {"auto": ALGO_AUTO, "vector": ALGO_VECTOR, "merge": ALGO_MERGE, "ro
 
 TUNE_A_EVICT_FIRST = 0x1
 TUNE_C_STREAMING = 0x2
-TUNE_NO_TAIL_SPLIT = 0x4
 TUNE_LITERAL = 0x80000000
 
 

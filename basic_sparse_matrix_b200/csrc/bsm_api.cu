@@ -569,34 +569,8 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_vector: kernel does not fit on an SM");
             const int ctas = tn.ctas_per_sm > 0 ? std::min(tn.ctas_per_sm, occ) : std::min(occ, 4);
             const int grid = (int)std::min<uint64_t>(p.num_super, (uint64_t)g_rt.sm_count * ctas);
-            // Wave quantisation: the persistent grid takes super-batches blockIdx, +grid, ... so a last round that
-            // fills only part of the grid costs a full round (a 1/8 row block of the headline matrix: 4.6 rounds paid
-            // as 5). Then the full rounds run as they are and the remaining rows go to a second launch with rows per
-            // warp cut so that they spread over the whole grid. Same kernel, same per-row arithmetic.
-            const uint64_t rounds = grid > 0 ? p.num_super / (uint64_t)grid : 0, rem = grid > 0 ? p.num_super % (uint64_t)grid : 0;
-            const bool split_tail = tn.rows_per_warp <= 0 && !(tn.flags & BSM_TUNE_NO_TAIL_SPLIT) && !multi && rounds >= 1 && rem > 0 &&
-                                    rem * 10 < (uint64_t)grid * 9 && p.P > p.R && rounds <= 16;
-            if (split_tail) {
-                const uint64_t main_rows = rounds * (uint64_t)grid * S, tail_rows = a->rows - main_rows;
-                RowParams pm = p;
-                pm.rows = (uint32_t)main_rows;
-                pm.num_super = (uint32_t)(rounds * (uint64_t)grid);
-                BSM_TRY(launch_spmm_rows(a->dtype, sh, pm, flavour, multi, grid, block, smem, ctas, g_rt.stream));
-                RowParams pt = p;
-                pt.row_ptr = p.row_ptr + main_rows;   // row_ptr values are absolute entry indices: col_idx / vals stay
-                pt.C = (char *)p.C + main_rows * (uint64_t)p.ldc * s;
-                pt.rows = (uint32_t)tail_rows;
-                const uint64_t per_warp = tail_rows / ((uint64_t)nw * (uint64_t)grid);   // rows per warp if every CTA gets one batch
-                pt.P = (uint32_t)std::min<uint64_t>(p.P, std::max<uint64_t>(p.R, per_warp / p.R * p.R));
-                const uint64_t St = (uint64_t)nw * pt.P;
-                pt.num_super = (uint32_t)((tail_rows + St - 1) / St);
-                const int grid_t = (int)std::min<uint64_t>(pt.num_super, (uint64_t)grid);
-                BSM_TRY(launch_spmm_rows(a->dtype, sh, pt, flavour, multi, grid_t, block, smem, ctas, g_rt.stream));
-                g_info.kernels += 2;
-            } else {
-                if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, flavour, multi, grid, block, smem, ctas, g_rt.stream));
-                g_info.kernels += grid > 0;
-            }
+            if (grid > 0) BSM_TRY(launch_spmm_rows(a->dtype, sh, p, flavour, multi, grid, block, smem, ctas, g_rt.stream));
+            g_info.kernels += grid > 0;
             g_info.vec_elems = sh.V;
             g_info.lanes_per_row = sh.G;
             g_info.reg_tiles = sh.NT;

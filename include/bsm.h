@@ -72,8 +72,6 @@ typedef enum bsm_algo {
 /* bsm_tuning.flags */
 #define BSM_TUNE_A_EVICT_FIRST 0x1u   /* L2 evict-first policy on the TMA bulk copies of col_idx/values */
 #define BSM_TUNE_C_STREAMING   0x2u   /* st.global.cs for C rows                                       */
-#define BSM_TUNE_NO_TAIL_SPLIT 0x4u   /* vector kernel: one launch even when the last round of super-batches fills only
-                                         part of the grid (default: those rows go to a second, finer-grained launch)  */
 #define BSM_TUNE_DEFAULT_FLAGS (BSM_TUNE_A_EVICT_FIRST | BSM_TUNE_C_STREAMING)
 
 /* Launch tuning; all-zero = library heuristics. Used by the bench sweeps and tests. */

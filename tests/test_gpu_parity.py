@@ -182,29 +182,6 @@ def test_vector_grouped_lanes_bitwise(gpu, dtype):
                     assert_bitwise(got, want, f"grouped m={m} n={n} G={g} NT={nt} {tune}")
 
 
-def test_vector_tail_split_is_bitwise_identical(gpu):
-    """Rows left over after the full rounds of the persistent grid go to a second, finer-grained launch: same result
-    as the single launch (flags = defaults | TUNE_NO_TAIL_SPLIT), bit for bit."""
-    g = 96                                                   # 884 736 rows: a few rounds plus a partial one
-    a = gpu.DeviceCsr.laplacian(g, g, g)
-    b = gpu.DeviceDense.generate(g ** 3, 128, seed=5, mode=gen.MODE_REAL)
-    c1 = a.mul_dense(b, algo="vector")
-    k1 = gpu.last_launch_info()["kernels"]
-    t = gpu.make_tuning("vector", flags=_lib.TUNE_A_EVICT_FIRST | _lib.TUNE_C_STREAMING | _lib.TUNE_NO_TAIL_SPLIT)
-    c2 = a.mul_dense(b, algo="vector", tuning=t)
-    assert gpu.last_launch_info()["kernels"] == 1
-    assert k1 in (1, 2)
-    assert_bitwise(c1.to_rowmajor(), c2.to_rowmajor(), f"tail split ({k1} launches) vs single launch")
-    v, ci, ri, _ = gen.laplacian(g, g, g)
-    ids = np.unique(np.random.default_rng(3).integers(0, g ** 3, 200).tolist() + [0, g ** 3 - 1, g ** 3 - 2])
-    want = np.stack([ref_numpy.mul_dense_rowmajor(v[ri[i]:ri[i + 1]], np.arange(ri[i + 1] - ri[i], dtype=np.uint64),
-                                                  np.array([0, ri[i + 1] - ri[i]], np.uint64),
-                                                  gen.dense_rows(g ** 3, 128, 5, gen.MODE_REAL, row_ids=ci[ri[i]:ri[i + 1]]))[0] for i in ids])
-    assert_bitwise(c1.to_rowmajor()[ids], want, "tail split vs oracle")
-    for h in (a, b, c1, c2):
-        h.close()
-
-
 def test_vector_slow_path_rows_longer_than_a_stage(gpu):
     rng = np.random.default_rng(9)
     m, k, n = 64, 5000, 32
