@@ -126,11 +126,13 @@ static int detect_row_stride(bsm_csr *a)
         uint32_t cols[64];
         BSM_CUDA(cudaMemcpyAsync(cols, a->col_idx + rp[0], len * 4, cudaMemcpyDeviceToHost, g_rt.stream));
         BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
-        std::sort(cols, cols + len);
-        const uint32_t med = cols[len / 2];
+        // smallest distance > 1 of a stored column from the diagonal (NOT from the row's median column: on a grid
+        // boundary row the median is a neighbour and the result is off by one — 4095 for a line of 4096)
+        const uint64_t diag = r + a->row_offset;
         uint32_t stride = 0;
         for (uint32_t i = 0; i < len; ++i) {
-            const uint32_t d = cols[i] > med ? cols[i] - med : med - cols[i];
+            const uint64_t d64 = cols[i] > diag ? cols[i] - diag : diag - cols[i];
+            const uint32_t d = (uint32_t)std::min<uint64_t>(d64, 0xFFFFFFFFull);
             if (d > 1 && (stride == 0 || d < stride)) stride = d;
         }
         if (stride < 16 || stride > 16384 || (found && stride != found)) return BSM_OK;
@@ -172,6 +174,7 @@ static int csr_upload_rows(int dtype, uint64_t rows_total, uint64_t cols, const 
     if (nnz && (!v || !col_index)) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_upload: null value/index arrays");
     bsm_csr *a = nullptr;
     BSM_TRY(alloc_csr(dtype, rows, cols, nnz, &a));
+    a->row_offset = row_begin;
     cudaStream_t sm = g_rt.stream;
     uint64_t *stage = nullptr;
     uint32_t *flags = nullptr;
@@ -515,6 +518,15 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
                 if (sh.G < 32) R = std::max(R, 4u * rpp);
             }
             R = std::max(rq, R / rq * rq);
+            // a stencil-like matrix: the slice must divide the line length, or the rows per warp (a multiple of the
+            // slice) stop matching the lines and the L1 sharing between the warps of a CTA is lost (measured on a
+            // 5-entry-per-row stencil, line 256: 24-row slices -> P = 264: 12.9 ms; 16-row slices -> P = 256: see
+            // profiles/r1_probe_near_diag.jsonl)
+            if (!user_R && a->row_stride >= 2 * rq && a->row_stride % R) {
+                uint32_t r2 = R;
+                while (r2 > rq && a->row_stride % r2) r2 -= rq;
+                if (a->row_stride % r2 == 0) R = r2;
+            }
 
             int flavour = pick_row_flavour(tn, sh, wide_full, grouped, grouped_by_default, multi);
             // warps per CTA: what the flavour was compiled for; fewer on small matrices, so that no SM idles behind a
@@ -1060,7 +1072,7 @@ static int mul_vector(const bsm_csr *a, int dtype, const T *rhs, uint64_t rhs_le
 }
 
 template <typename CountFn, typename FillFn>
-static int gen_counted(int dtype, uint64_t rows, uint64_t cols, uint64_t max_per_row, CountFn count_fn, FillFn fill_fn, bsm_csr **out)
+static int gen_counted(int dtype, uint64_t rows, uint64_t cols, uint64_t max_per_row, uint64_t row_begin, CountFn count_fn, FillFn fill_fn, bsm_csr **out)
 {
     BSM_TRY(ensure_init());
     if (!out) return fail(BSM_ERR_INVALID_ARGUMENT, "gen: null out");
@@ -1080,6 +1092,7 @@ static int gen_counted(int dtype, uint64_t rows, uint64_t cols, uint64_t max_per
         BSM_CUDA(cudaMemcpyAsync(&nnz, counts + rows, 4, cudaMemcpyDeviceToHost, sm));
         BSM_CUDA(cudaStreamSynchronize(sm));
         BSM_TRY(alloc_csr(dtype, rows, cols, nnz, &a));
+        a->row_offset = row_begin;
         BSM_CUDA(cudaMemcpyAsync(a->row_ptr, counts, (rows + 1) * 4, cudaMemcpyDeviceToDevice, sm));
         BSM_TRY(fill_fn(a, sm));
         return compute_stats(a);
@@ -1576,7 +1589,7 @@ int bsm_gen_laplacian(int dtype, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t
     const uint64_t n = nx * ny * nz;
     if (row_begin > row_end || row_end > n) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_laplacian: bad row range");
     return gen_counted(
-        dtype, row_end - row_begin, n, 1 + 2 * ((nx > 1) + (ny > 1) + (nz > 1)),
+        dtype, row_end - row_begin, n, 1 + 2 * ((nx > 1) + (ny > 1) + (nz > 1)), row_begin,
         [&](uint32_t *counts, cudaStream_t sm) { return launch_laplacian_counts(nx, ny, nz, row_begin, row_end, counts, sm); },
         [&](bsm_csr *a, cudaStream_t sm) {
             return launch_laplacian_fill(dtype, nx, ny, nz, row_begin, row_end, a->row_ptr, a->col_idx, a->vals, sm);
@@ -1588,7 +1601,7 @@ int bsm_gen_band(int dtype, uint64_t n, uint64_t hb, uint64_t row_begin, uint64_
 {
     if (n == 0 || row_begin > row_end || row_end > n) return fail(BSM_ERR_INVALID_ARGUMENT, "gen_band: bad arguments");
     return gen_counted(
-        dtype, row_end - row_begin, n, 2 * hb + 1,
+        dtype, row_end - row_begin, n, 2 * hb + 1, row_begin,
         [&](uint32_t *counts, cudaStream_t sm) { return launch_band_counts(n, hb, row_begin, row_end, counts, sm); },
         [&](bsm_csr *a, cudaStream_t sm) {
             return launch_band_fill(dtype, n, hb, row_begin, row_end, a->row_ptr, a->col_idx, a->vals, sm);

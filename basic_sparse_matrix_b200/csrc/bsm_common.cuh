@@ -63,6 +63,7 @@ struct bsm_csr {
     bool cache_pooled = false;     // likewise for the merge-path caches below
     uint64_t max_row_nnz = 0;      // csr_row_stats (dispatch heuristic)
     uint32_t col_min = 0, col_max = 0;   // smallest / largest stored column (valid when nnz > 0)
+    uint64_t row_offset = 0;       // global index of local row 0 (row blocks of a partitioned matrix keep global columns)
     uint32_t row_stride = 0;       // dominant off-diagonal column stride of a stencil-like matrix (0 = none)
     // row-block probe (spmm_rowblock.cu), run on first use: 0 = not probed, 1 = every row is a run of consecutive
     // columns, 2 = not; rowblock_union = B rows the row-block kernel would load (vs nnz for the vector kernel)
