@@ -460,6 +460,9 @@ static uint32_t pick_rows_per_warp(const bsm_csr *a, const bsm_tuning &tn, const
         P = best_p ? best_p : R;
         if (a->rows / ((uint64_t)nw * P) < (uint64_t)g_rt.sm_count) P = R;
     }
+    // flat-stream shapes take any P >= R (the last slice of a line may be short; the row_ptr windows are realigned in
+    // the kernel); the row-by-row narrow shapes keep whole slices
+    if (sh.G == 32 || sh.NT > 1) return std::max(R, P);
     return std::max(R, (P + R - 1) / R * R);
 }
 

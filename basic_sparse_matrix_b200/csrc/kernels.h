@@ -22,7 +22,7 @@ struct RowParams {
     uint32_t rows;
     uint32_t n;      // columns in this pass
     uint32_t ldb, ldc;
-    uint32_t P;          // consecutive rows owned by one warp inside a super-batch (multiple of R)
+    uint32_t P;          // consecutive rows owned by one warp inside a super-batch (>= R; a multiple of R for the row-by-row shapes)
     uint32_t R;          // rows per TMA slice of one warp (multiple of 4 and of 32/G)
     uint32_t num_super;  // super-batches = ceil(rows / (warps * P))
     uint32_t cap;        // staged entries per slice (multiple of 4)

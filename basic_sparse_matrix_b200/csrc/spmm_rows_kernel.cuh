@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
 
     const T *__restrict__ vals = static_cast<const T *>(p.vals);
     const uint32_t S = W * p.P;                 // rows per super-batch
-    const uint32_t spw = p.P / p.R;             // slices per warp per super-batch
+    const uint32_t spw = (p.P + p.R - 1) / p.R; // slices per warp per super-batch (the last one is short when R does not divide P)
     const uint32_t my_supers = blockIdx.x < p.num_super ? (p.num_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     const uint32_t my_slices = my_supers * spw;
 
@@ -150,11 +150,15 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
     // a tight register budget: the slice position is recomputed from the slice index (measured 3-4 % faster
     // there than cursors). Narrow shapes (G < 32) have short slices — a few row passes — and registers to
     // spare: incremental cursors, no divisions in the loop (SpMV 0.078 -> 0.063 ms).
+    // P (rows per warp) is the line length of a stencil matrix and need be a multiple of neither R nor 4: the
+    // row_ptr window of a slice is copied from the 16-byte aligned index below its first row.
     if constexpr (G == 32 || NT > 1) {
-        // first row of this warp's i-th slice
-        auto slice_row0 = [&](uint32_t i) -> uint64_t {
+        // first row and row count of this warp's i-th slice (0 rows: past the end of the matrix)
+        auto slice_pos = [&](uint32_t i, uint64_t &r0, uint32_t &nr) {
             const uint32_t k = i / spw, t = i - k * spw;
-            return (uint64_t)(blockIdx.x + k * gridDim.x) * S + (uint64_t)warp * p.P + (uint64_t)t * p.R;
+            r0 = (uint64_t)(blockIdx.x + k * gridDim.x) * S + (uint64_t)warp * p.P + (uint64_t)t * p.R;
+            const uint32_t in_p = min(p.R, p.P - t * p.R);
+            nr = r0 < p.rows ? (uint32_t)min((uint64_t)in_p, p.rows - r0) : 0u;
         };
 
         // ---- producer side (lane 0): TMA bulk copies of one slice into ring stage i % stages --------
@@ -162,27 +166,30 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
         uint32_t pf_s = 0, pf_e = 0;                // entry range of the next slice to issue (prefetched)
         auto prefetch_bounds = [&](uint32_t i) {
             if (i < my_slices) {
-                const uint64_t r0 = slice_row0(i);
-                if (r0 < p.rows) {
-                    const uint32_t r1 = (uint32_t)min(r0 + p.R, (uint64_t)p.rows);
+                uint64_t r0;
+                uint32_t nr;
+                slice_pos(i, r0, nr);
+                if (nr) {
                     pf_s = __ldg(p.row_ptr + r0);
-                    pf_e = __ldg(p.row_ptr + r1);
+                    pf_e = __ldg(p.row_ptr + r0 + nr);
                 }
             }
         };
         auto issue = [&](uint32_t i) {
             // only lane 0 calls this
-            const uint64_t r0 = slice_row0(i);
-            if (r0 < p.rows) {
-                const uint32_t nr = (uint32_t)min((uint64_t)p.R, p.rows - r0);
+            uint64_t r0;
+            uint32_t nr;
+            slice_pos(i, r0, nr);
+            if (nr) {
                 const uint32_t stage = i % p.stages;
                 unsigned char *st = ring + (size_t)stage * L.stage_bytes;
                 const uint32_t base = pf_s & ~3u;                     // 16-byte aligned start for u32 and T
                 const uint32_t cnt = STAGED ? ((pf_e - base + 3u) & ~3u) : 0u;   // entries, multiple of 4
                 if (STAGED && cnt > p.cap) __trap();   // the host sizes cap from the longest row; never overrun the stage
-                const uint32_t cnt_r = (nr + 1u + 3u) & ~3u;          // row_ptr window rp[r0 .. r0+nr]
+                const uint32_t a0 = (uint32_t)(r0 & 3u);              // row_ptr window from the aligned index below r0
+                const uint32_t cnt_r = (a0 + nr + 1u + 3u) & ~3u;     // rp[r0 - a0 .. r0 + nr], at most R + 4 entries
                 mbar_arrive_expect_tx(&full_bar[stage], cnt_r * 4u + cnt * (4u + (uint32_t)sizeof(T)));
-                bulk_g2s(st + L.rp_off, p.row_ptr + r0, cnt_r * 4u, &full_bar[stage], policy);
+                bulk_g2s(st + L.rp_off, p.row_ptr + (r0 - a0), cnt_r * 4u, &full_bar[stage], policy);
                 if (cnt) {
                     bulk_g2s(st + L.idx_off, p.col_idx + base, cnt * 4u, &full_bar[stage], policy);
                     bulk_g2s(st + L.vals_off, vals + base, cnt * (uint32_t)sizeof(T), &full_bar[stage], policy);
@@ -210,15 +217,16 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
             __syncwarp();   // every lane is done reading the stage that is refilled next
             if (lane == 0 && i + p.stages - 1 < my_slices) issue(i + p.stages - 1);
 
-            const uint64_t row0_64 = slice_row0(i);
-            if (row0_64 < p.rows) {
+            uint64_t row0_64;
+            uint32_t nr;
+            slice_pos(i, row0_64, nr);
+            if (nr) {
                 const uint32_t row0 = (uint32_t)row0_64;
-                const uint32_t nr = min(p.R, p.rows - row0);
                 const uint32_t stage = i % p.stages;
                 mbar_wait(&full_bar[stage], (i / p.stages) & 1u);   // TMA bytes of this slice have landed
 
                 const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
-                const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off);
+                const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off) + (row0 & 3u);
                 if constexpr (STAGED)
                     process_slice<T, V, G, NT, FULLN, U, VECA, MULTI>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                                 reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,

@@ -64,6 +64,9 @@ WORKLOADS = {
     "laplace3d_256_n128_f32": ("laplace3d", dict(g=256), 128, "f32"),
     "laplace3d_256_n8_f64": ("laplace3d", dict(g=256), 8, "f64"),
     "laplace2d_4096_n64_f64": ("laplace2d", dict(g=4096), 64, "f64"),   # 5 entries per row, line length 4096
+    "laplace3d_252_n128_f64": ("laplace3d", dict(g=252), 128, "f64"),   # line lengths that are not powers of two
+    "laplace3d_250_n128_f64": ("laplace3d", dict(g=250), 128, "f64"),
+    "laplace3d_252_n64_f64": ("laplace3d", dict(g=252), 64, "f64"),
     # uniformly random columns, Poisson(8) rows: regular row lengths without any locality in B
     "uniform22_n64_f64": ("rmat", dict(scale=22, edges=8 << 22, a=0.25, b=0.25, c=0.25), 64, "f64"),
     "uniform22_n32_f64": ("rmat", dict(scale=22, edges=8 << 22, a=0.25, b=0.25, c=0.25), 32, "f64"),

@@ -119,7 +119,10 @@ def test_vector_tuning_variants_are_bitwise_identical(gpu, dtype):
                  dict(warps_per_cta=2), dict(warps_per_cta=16, ctas_per_sm=1), dict(flags=_lib.TUNE_LITERAL),
                  dict(rows_per_warp=64, rows_per_slice=16), dict(rows_per_warp=96, rows_per_slice=8, reg_flavour=2),
                  dict(rows_per_warp=32, rows_per_slice=32, warps_per_cta=4, reg_flavour=3),
-                 dict(rows_per_warp=512, rows_per_slice=4, stages=4, reg_flavour=4), dict(reg_flavour=1, stages=8)):
+                 dict(rows_per_warp=512, rows_per_slice=4, stages=4, reg_flavour=4), dict(reg_flavour=1, stages=8),
+                 # rows per warp that are a multiple of neither the slice nor 4 (short last slice, realigned row_ptr windows)
+                 dict(rows_per_warp=50, rows_per_slice=16), dict(rows_per_warp=33, rows_per_slice=8, reg_flavour=5),
+                 dict(rows_per_warp=251, rows_per_slice=32, lanes_per_row=32), dict(rows_per_warp=17, rows_per_slice=16, lanes_per_row=16)):
         got, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", **tune)
         assert_bitwise(got, want, f"tuning {tune}")
 
@@ -180,6 +183,23 @@ def test_vector_grouped_lanes_bitwise(gpu, dtype):
                     if mi == 0:   # (a giant row that cannot be staged falls back to a warp per row — by design)
                         assert (info["lanes_per_row"], info["reg_tiles"]) == (g, nt), info
                     assert_bitwise(got, want, f"grouped m={m} n={n} G={g} NT={nt} {tune}")
+
+
+@pytest.mark.parametrize("g", [50, 37])
+def test_vector_stencil_line_length_not_a_multiple_of_four(gpu, g):
+    """3-D Laplacian on a g^3 grid with g = 50 / 37: the rows per warp follow the line length (50, 37), so warps start
+    on rows that are not multiples of 4 and the last slice of a line is short. Bit-exact against the oracle."""
+    a = gpu.DeviceCsr.laplacian(g, g, g)
+    v, ci, ri, _ = gen.laplacian(g, g, g)
+    for n in (64, 128, 32):
+        b = gpu.DeviceDense.generate(g ** 3, n, seed=5, mode=gen.MODE_REAL)
+        c = a.mul_dense(b, algo="vector")
+        info = gpu.last_launch_info()
+        want = ref_numpy.mul_dense_rowmajor(v, ci, ri, gen.dense_rows(g ** 3, n, 5, gen.MODE_REAL))
+        assert_bitwise(c.to_rowmajor(), want, f"laplacian {g}^3 n={n} launched {info}")
+        for h in (b, c):
+            h.close()
+    a.close()
 
 
 def test_vector_slow_path_rows_longer_than_a_stage(gpu):
