@@ -135,6 +135,14 @@ static int detect_row_stride(bsm_csr *a)
             const uint32_t d = (uint32_t)std::min<uint64_t>(d64, 0xFFFFFFFFull);
             if (d > 1 && (stride == 0 || d < stride)) stride = d;
         }
+        // a box stencil (9- / 27-point) also stores the neighbours of the line neighbour: distances nx-1, nx, nx+1 -> nx
+        bool plus1 = false, plus2 = false;
+        for (uint32_t i = 0; i < len && stride; ++i) {
+            const uint64_t d64 = cols[i] > diag ? cols[i] - diag : diag - cols[i];
+            plus1 |= d64 == (uint64_t)stride + 1;
+            plus2 |= d64 == (uint64_t)stride + 2;
+        }
+        if (plus1 && plus2) stride += 1;
         if (stride < 16 || stride > 16384 || (found && stride != found)) return BSM_OK;
         found = stride;
     }
