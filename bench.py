@@ -63,6 +63,8 @@ WORKLOADS = {
     "laplace3d_256_n16_f64": ("laplace3d", dict(g=256), 16, "f64"),
     "laplace3d_256_n128_f32": ("laplace3d", dict(g=256), 128, "f32"),
     "laplace3d_256_n8_f64": ("laplace3d", dict(g=256), 8, "f64"),
+    "laplace3d_256_n1_f64": ("laplace3d", dict(g=256), 1, "f64"),     # SpMV on the headline matrix
+    "laplace3d_256_n4_f64": ("laplace3d", dict(g=256), 4, "f64"),
     "laplace2d_4096_n64_f64": ("laplace2d", dict(g=4096), 64, "f64"),   # 5 entries per row, line length 4096
     "laplace3d_252_n128_f64": ("laplace3d", dict(g=252), 128, "f64"),   # line lengths that are not powers of two
     "laplace3d_250_n128_f64": ("laplace3d", dict(g=250), 128, "f64"),
