@@ -247,27 +247,39 @@ __device__ __forceinline__ double mul_add_fused(double a, double b, double acc) 
 __device__ __forceinline__ float mul_add_fused(float a, float b, float acc) { return fmaf(a, b, acc); }
 
 // acc += a * b over a lane's V elements, product and sum rounded separately (as mul_add_unfused). f32 with an even V
-// uses Blackwell's packed multiply: one FMUL2 per two products, then scalar FADDs — 3 instructions per two elements
-// instead of 4. (A packed add after the packed multiply is NOT used: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
-// into one FFMA2, i.e. a fused multiply-add; tests/test_build_flags.py checks the SASS for that.)
-template <typename T, int V> __device__ __forceinline__ void axpy_unfused(T a, const T (&b)[V], T (&acc)[V])
+// uses Blackwell's packed f32x2 pipe at two instructions per two elements:
+//     q   = fma.rn.f32x2(a, b, -0.0)   == rn(a*b) exactly (an FMA whose addend is -0.0 rounds the exact product once
+//                                         and keeps its sign, also for zero products) -> FFMA2
+//     acc = add.rn.f32x2(acc, q)        -> FADD2
+// A packed MULTIPLY feeding the packed add is NOT usable: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2,
+// a fused multiply-add with a single rounding. `negzero2` = two -0.0f, built from a value the compiler cannot see
+// through (else it folds x + -0.0 and contracts again); tests/test_build_flags.py checks the shipped SASS
+// (FFMA2 and FADD2 in equal numbers, no scalar FFMA), the bitwise parity tests check the arithmetic.
+template <typename T, int V> __device__ __forceinline__ void axpy_unfused(T a, const T (&b)[V], T (&acc)[V], unsigned long long negzero2)
 {
     if constexpr (sizeof(T) == 4 && V % 2 == 0) {
 #pragma unroll
         for (int i = 0; i < V; i += 2) {
-            unsigned long long aa, bb, pp;
-            float p0, p1;
+            unsigned long long aa, bb, cc, qq;
             asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
             asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[i]), "f"(b[i + 1]));
-            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(pp) : "l"(aa), "l"(bb));
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(pp));
-            acc[i] = __fadd_rn(acc[i], p0);
-            acc[i + 1] = __fadd_rn(acc[i + 1], p1);
+            asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i]), "f"(acc[i + 1]));
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(qq) : "l"(aa), "l"(bb), "l"(negzero2));
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(cc) : "l"(cc), "l"(qq));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i]), "=f"(acc[i + 1]) : "l"(cc));
         }
     } else {
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = mul_add_unfused(a, b[i], acc[i]);
     }
+}
+// two -0.0f; `runtime_zero` must be 0 at run time and opaque at compile time (a kernel parameter bit that is never set)
+__device__ __forceinline__ unsigned long long packed_negzero(uint32_t runtime_zero)
+{
+    unsigned long long r;
+    const uint32_t nz = 0x80000000u | runtime_zero;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "r"(nz));
+    return r;
 }
 
 template <bool FUSED, typename T> __device__ __forceinline__ T mul_add(T a, T b, T acc)

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
     const uint32_t ldb_bytes = p.ldb * (uint32_t)sizeof(T), ldc_bytes = p.ldc * (uint32_t)sizeof(T);
     const bool streaming = (p.flags & BSM_TUNE_C_STREAMING) != 0;
     const uint64_t policy = (p.flags & BSM_TUNE_A_EVICT_FIRST) ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const unsigned long long negzero2 = packed_negzero(p.flags >> 31);   // (bit 31 of the flags is never set: the host masks it)
     uint32_t phase = 0;
 
     // neighbouring warps take neighbouring warp blocks: their B ranges overlap and meet in L1
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
                 for (int r = 0; r < RB; ++r) {
                     const uint32_t off = j - first[r];
                     if (off < len[r]) {   // row r stores column j, at entry base + off; ascending j = stored order
-                        axpy_unfused<T, V>(va[base[r] + off], b.x, acc[r].x);
+                        axpy_unfused<T, V>(va[base[r] + off], b.x, acc[r].x, negzero2);
                     }
                 }
             }
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
                     if (col_ok) b.template load<false>(reinterpret_cast<const T *>(brow), 0ull);
 #pragma unroll
                     for (int r = 0; r < RB; ++r) {
-                        axpy_unfused<T, V>(vrow[r][j], b.x, acc[r].x);
+                        axpy_unfused<T, V>(vrow[r][j], b.x, acc[r].x, negzero2);
                     }
                 }
             }

@@ -2,7 +2,9 @@
 
 The reference computes `value = value + (a * b)` with two roundings (src/sparse.rs:438-439); nvcc never
 contracts the _rn intrinsics, but ptxas DOES contract a packed mul.rn.f32x2 feeding an add.rn.f32x2 into one
-FFMA2, which is why the kernels use the packed multiply with scalar adds only. This checks the shipped SASS."""
+FFMA2. The row-block kernel therefore forms its f32 products as fma.rn.f32x2(a, b, -0.0) (== rn(a*b)) followed
+by add.rn.f32x2: in its SASS every FFMA2 must be paired with an FADD2 and there must be no scalar FFMA; the
+vector kernel must contain no fused multiply-add at all. This checks the shipped SASS."""
 import os
 import re
 import shutil
@@ -17,18 +19,25 @@ from basic_sparse_matrix_b200 import _lib
 def test_no_fused_multiply_add_in_the_bit_exact_kernels():
     assert os.path.exists(_lib.LIB_PATH), "build the native library first (__graft_entry__.build())"
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], check=True, capture_output=True, text=True).stdout
-    current, fused, seen = None, {}, set()
+    current, fused, seen, packed = None, {}, set(), {}
     for line in sass.splitlines():
         m = re.search(r"Function : (\S+)", line)
         if m:
             current = m.group(1)
             continue
-        if current and ("spmm_rows_kernel" in current or "spmm_rowblock_kernel" in current):
-            seen.add(current)
-            if re.search(r"\b(FFMA2?|DFMA|HFMA2)\b", line) and "HFMA2.MMA" not in line:
-                fused.setdefault(current, []).append(line.strip()[:80])
+        if not current or not ("spmm_rows_kernel" in current or "spmm_rowblock_kernel" in current):
+            continue
+        seen.add(current)
+        op = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if not op:
+            continue
+        name = op.group(1).split(".")[0]
+        if name in ("FFMA2", "FADD2") and "spmm_rowblock_kernel" in current:
+            packed.setdefault(current, {"FFMA2": 0, "FADD2": 0})[name] += 1
+        elif name in ("FFMA", "FFMA2", "DFMA"):
+            fused.setdefault(current, []).append(line.strip()[:80])
     assert len(seen) > 50, "kernels not found in the SASS dump"
-    # (HFMA2 / FFMA with constant operands are ptxas idioms for moving immediates; a real product has register operands)
-    real = {k: [l for l in v if not re.search(r"(HFMA2|FFMA)\S* R\d+, -?RZ|, RZ, ", l)] for k, v in fused.items()}
-    real = {k: v for k, v in real.items() if v}
-    assert not real, {k: v[:2] for k, v in list(real.items())[:3]}
+    assert not fused, {k: v[:2] for k, v in list(fused.items())[:3]}
+    assert packed, "the f32 row-block kernels should use the packed f32x2 pipe"
+    for k, c in packed.items():
+        assert c["FFMA2"] == c["FADD2"], (k, c)   # every product-forming FFMA2 is followed by its separate FADD2
