@@ -78,7 +78,8 @@ typedef enum bsm_algo {
 typedef struct bsm_tuning {
     int32_t algo;            /* bsm_algo                                                            */
     int32_t col_tile;        /* columns per pass over A (0 = heuristic, -1 = all n in one pass)     */
-    int32_t rows_per_slice;  /* vector kernel: rows of one warp staged per TMA slice (0 = heuristic)*/
+    int32_t rows_per_slice;  /* vector kernel: rows of one warp staged per TMA slice (0 = heuristic);
+                                row-block kernel: rows per lane group, 4 or 8 (else heuristic)       */
     int32_t stages;          /* vector kernel: TMA ring depth per warp (0 = heuristic)              */
     int32_t warps_per_cta;   /* compute warps per CTA (0 = heuristic)                               */
     int32_t ctas_per_sm;     /* persistent grid = SMs x this (0 = heuristic)                        */
