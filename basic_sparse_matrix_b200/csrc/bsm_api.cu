@@ -390,7 +390,20 @@ struct ScatterTargets {
 // ---- launch plan of the vector kernel for one column pass ------------------------------------------------
 // Every default below comes from a same-box A/B sweep kept in profiles/ (tools/sweep.py); bsm_tuning overrides each.
 
-static double mean_row_nnz(const bsm_csr *a) { return a->rows ? (double)a->nnz / (double)a->rows : 0.0; }
+// What the planner knows about the matrix and the device — no pointers, no CUDA calls, so the same code plans a
+// launch for bsm_spmm and answers bsm_plan_vector (a dry run the CPU test-suite uses to pin the heuristics).
+struct MatrixFacts {
+    int dtype;
+    uint64_t rows, nnz, max_row_nnz;
+    uint32_t row_stride;   // line length of a stencil-like matrix (0 = none)
+    double mean() const { return rows ? (double)nnz / (double)rows : 0.0; }
+};
+struct DeviceFacts {
+    int sm_count;
+    size_t smem_max;       // dynamic shared memory one CTA may use
+};
+static MatrixFacts facts_of(const bsm_csr *a) { return MatrixFacts{a->dtype, a->rows, a->nnz, a->max_row_nnz, a->row_stride}; }
+static double mean_row_nnz(const bsm_csr *a) { return facts_of(a).mean(); }
 
 // Grouped lanes: fewer lanes per row than the 128-bit loads need -> 2 or 4 register tiles per lane and 32/G rows side
 // by side, every lane group walking its own flat entry stream over a run of consecutive rows (one LDS of the staged A
@@ -403,13 +416,13 @@ static double mean_row_nnz(const bsm_csr *a) { return a->rows ? (double)a->nnz /
 //     128-byte rows (x16 f64), short rows: 8 -> 4 lanes x 2 tiles                      2.70 -> 1.37 ms
 //   (the row-by-row walk of narrow shapes drains its gather window at every row end; rows of ~65 entries, the band
 //   matrix x32 f32, are still faster row by row: 0.45 vs 0.72 ms)
-static bool regroup_lanes(const bsm_csr *a, const bsm_tuning &tn, uint32_t n, size_t s, bool allowed, Shape &sh, bool &by_default)
+static bool regroup_lanes(const MatrixFacts &m, const bsm_tuning &tn, uint32_t n, size_t s, bool allowed, Shape &sh, bool &by_default)
 {
-    const double mean = mean_row_nnz(a);
+    const double mean = m.mean();
     int want_g = tn.lanes_per_row;
     by_default = false;
     if (want_g == 0 && sh.NT == 1 && tn.reg_flavour <= 0 && tn.warps_per_cta <= 0 && tn.prefer_wide_rows == 0 &&
-        (double)a->max_row_nnz <= 4.0 * mean + 8.0) {
+        (double)m.max_row_nnz <= 4.0 * mean + 8.0) {
         if (sh.G == 32) want_g = 8;
         else if ((sh.G == 16 || sh.G == 8) && mean <= 32.0) want_g = sh.G / 2;
         by_default = want_g > 0;
@@ -442,22 +455,22 @@ static int pick_row_flavour(const bsm_tuning &tn, const Shape &sh, bool wide_ful
 
 // Rows per warp inside a super-batch: the dominant row stride of a stencil-like matrix (so the warps of a CTA sweep
 // adjacent grid lines), else one slice (a few slices for narrow shapes on large matrices: measured on band x 32).
-static uint32_t pick_rows_per_warp(const bsm_csr *a, const bsm_tuning &tn, const Shape &sh, uint32_t R, int nw, int resident)
+static uint32_t pick_rows_per_warp(const MatrixFacts &m, const DeviceFacts &dev, const bsm_tuning &tn, const Shape &sh, uint32_t R, int nw, int resident)
 {
     uint32_t P = R;
-    if (tn.rows_per_warp <= 0 && sh.G < 32 && a->rows / ((uint64_t)nw * 4 * R) >= 4ull * g_rt.sm_count) P = 4 * R;
+    if (tn.rows_per_warp <= 0 && sh.G < 32 && m.rows / ((uint64_t)nw * 4 * R) >= 4ull * dev.sm_count) P = 4 * R;
     if (tn.rows_per_warp > 0) {
         P = (uint32_t)tn.rows_per_warp;
-    } else if (a->row_stride >= 2 * R) {
+    } else if (m.row_stride >= 2 * R) {
         // P = stride / m keeps warps w and w+m on adjacent lines. Among stride, stride/2, stride/4, ... pick the one that
         // wastes least to wave quantisation (rounds x rows per warp per round); a larger P wins unless a smaller one
         // saves more than 10 % (measured on 1/8 and 1/4 row blocks: profiles/r1_sweepk_l3d_n128_s8.jsonl — locality
         // beats balance). Too few rows for even one round per SM: plain slices.
-        const uint64_t grid_est = (uint64_t)g_rt.sm_count * resident;
+        const uint64_t grid_est = (uint64_t)dev.sm_count * resident;
         double best_cost = 0.0;
         uint32_t best_p = 0;
-        for (uint32_t cand = a->row_stride; cand >= 2 * R; cand /= 2) {
-            const uint64_t supers = (a->rows + (uint64_t)nw * cand - 1) / ((uint64_t)nw * cand);
+        for (uint32_t cand = m.row_stride; cand >= 2 * R; cand /= 2) {
+            const uint64_t supers = (m.rows + (uint64_t)nw * cand - 1) / ((uint64_t)nw * cand);
             const double cost = (double)((supers + grid_est - 1) / grid_est) * cand;
             if (best_p == 0 || cost < 0.90 * best_cost) {
                 best_cost = cost;
@@ -466,12 +479,127 @@ static uint32_t pick_rows_per_warp(const bsm_csr *a, const bsm_tuning &tn, const
             if (cand % 2) break;
         }
         P = best_p ? best_p : R;
-        if (a->rows / ((uint64_t)nw * P) < (uint64_t)g_rt.sm_count) P = R;
+        if (m.rows / ((uint64_t)nw * P) < (uint64_t)dev.sm_count) P = R;
     }
     // flat-stream shapes take any P >= R (the last slice of a line may be short; the row_ptr windows are realigned in
     // the kernel); the row-by-row narrow shapes keep whole slices
     if (sh.G == 32 || sh.NT > 1) return std::max(R, P);
     return std::max(R, (P + R - 1) / R * R);
+}
+
+struct PassAlign {       // what pick_shape needs to know about the operands of one column pass
+    uint64_t ldb, ldc, col0;
+    const void *b, *c;
+};
+struct VectorPlan {
+    Shape sh;
+    bool grouped = false;
+    int flavour = 0, nw = 0;
+    uint32_t R = 0, P = 0, stages = 0, cap = 0, num_super = 0;
+    size_t smem = 0;
+    int resident = 1;    // CTAs per SM the flavour targets
+};
+
+// Launch plan of the vector kernel for one pass of n columns. Pure host arithmetic.
+static int plan_vector_pass(const MatrixFacts &m, const DeviceFacts &dev, const bsm_tuning &tn, uint32_t n, const PassAlign &al, bool scatter,
+                            bool multi, VectorPlan *out)
+{
+    const size_t s = dtype_size(m.dtype);
+    const double mean = m.mean();
+    const bool user_R = tn.rows_per_slice > 0, user_nw = tn.warps_per_cta > 0, user_stages = tn.stages > 0;
+    const size_t smem_max = dev.smem_max;
+    RowParams p{};   // geometry fields only (row_kernel_smem_bytes reads cap, R, stages)
+    // second attempt = without grouped lanes, when their (always staged) slices do not fit shared memory
+    for (bool allow_grouped = true;; allow_grouped = false) {
+        Shape sh = pick_shape(n, al.ldb, al.ldc, al.col0, al.b, al.c, s, tn.prefer_wide_rows != 0);
+        bool grouped_by_default = false;
+        const bool grouped = regroup_lanes(m, tn, n, s, allow_grouped && !scatter, sh, grouped_by_default);
+        const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
+        const uint32_t rpp = 32u / (uint32_t)sh.G;   // rows side by side in one warp
+        const uint32_t rq = std::max(4u, rpp);       // slice granularity (rpp is a power of two)
+
+        // rows per TMA slice: ~128 entries per bulk copy (~224 with one register tile per lane, r1_sweepi_*, and for
+        // 8 lanes x 2 tiles); narrow shapes want several row passes per slice to amortise the slice bookkeeping
+        uint32_t R;
+        if (user_R) {
+            R = (uint32_t)tn.rows_per_slice;
+        } else {
+            const double target = ((sh.G == 32 && sh.NT == 1) || (grouped && grouped_by_default && sh.NT == 2)) ? 224.0 : 128.0;
+            R = (uint32_t)std::min<double>(256.0, std::max(1.0, target / std::max(1.0, mean)));
+            if (sh.G < 32) R = std::max(R, 4u * rpp);
+        }
+        R = std::max(rq, R / rq * rq);
+        // a stencil-like matrix: the slice must divide the line length, or the rows per warp (a multiple of the
+        // slice) stop matching the lines and the L1 sharing between the warps of a CTA is lost (measured on a
+        // 5-entry-per-row stencil, line 256: 24-row slices -> P = 264: 12.9 ms; 16-row slices -> P = 256: see
+        // profiles/r1_probe_near_diag.jsonl)
+        // (a divisor down to half the target; failing that the last slice of every line is short — a line of 100
+        // keeps 16-row slices, 6 x 16 + 4, rather than dropping to 4-row slices)
+        if (!user_R && m.row_stride >= 2 * rq && m.row_stride % R) {
+            uint32_t r2 = R;
+            while (r2 > rq && 2 * r2 > R && m.row_stride % r2) r2 -= rq;
+            if (m.row_stride % r2 == 0) R = r2;
+        }
+
+        int flavour = pick_row_flavour(tn, sh, wide_full, grouped, grouped_by_default, multi);
+        // warps per CTA: what the flavour was compiled for; fewer on small matrices, so that no SM idles behind a
+        // handful of fat super-batches
+        const bool big_cta = (wide_full && (flavour == 5 || flavour == 6 || flavour == 7)) || (grouped && flavour == 6);
+        const int max_warps = big_cta ? 24 : ((flavour >= 2 && (wide_full || grouped)) ? 8 : 16);
+        int nw = user_nw ? std::min(tn.warps_per_cta, 24) : (big_cta ? 24 : 16);
+        if (!user_nw) {
+            const uint64_t rows_per_warp_min = big_cta ? R : rq;
+            const int nw_floor = big_cta ? 3 : 2;
+            while (nw > nw_floor && (uint64_t)nw * rows_per_warp_min * (uint64_t)dev.sm_count > m.rows) nw /= 2;
+        }
+        nw = std::min(nw, max_warps);
+
+        // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start, + slack: the
+        // vectorised A-stream reads run up to two gather windows past the slice). Shrink, in this order, the ring
+        // depth, the slice and the CTA until the rings fit: first under a soft limit that leaves most of the 228 KB
+        // to L1 (where wide B rows live), then under the hardware limit. If even the smallest slice cannot be
+        // staged, col_idx / values are read from global memory instead (unstaged variant).
+        const int resident = ((wide_full || grouped) && (flavour == 2 || flavour == 4)) ? 3 : 1;   // CTAs per SM the flavour targets
+        const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (160 * 1024) / resident);
+        const uint32_t window = flavour == 7 ? 10u : (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight
+        const uint32_t r_floor = sh.G < 32 ? std::max(rq, 2u * rpp) : rq;
+        p.R = R;
+        p.stages = user_stages ? (uint32_t)std::min(tn.stages, 8) : (grouped && grouped_by_default && sh.G >= 8 ? 2u : 3u);
+        auto smem_now = [&]() {
+            p.cap = (uint32_t)pad4((uint64_t)p.R * m.max_row_nnz + 3) + 2 * window + 4;
+            return row_kernel_smem_bytes(m.dtype, p, nw);
+        };
+        size_t smem = smem_now();
+        while (smem > smem_soft && p.stages > 2 && !user_stages) { --p.stages; smem = smem_now(); }
+        while (smem > smem_soft && p.R > r_floor && !user_R) { p.R = std::max(r_floor, p.R / 2 / rq * rq); smem = smem_now(); }
+        while (smem > smem_soft && nw > 8 && !user_nw) { nw /= 2; smem = smem_now(); }
+        while (smem > smem_max && p.stages > 1) { --p.stages; smem = smem_now(); }
+        while (smem > smem_max && p.R > rq && !user_R) { p.R = std::max(rq, p.R / 2 / rq * rq); smem = smem_now(); }
+        while (smem > smem_max && nw > 2 && !user_nw) { nw /= 2; smem = smem_now(); }
+        if (smem > smem_max && grouped) continue;   // the grouped shapes have no unstaged variant: a warp per row instead
+        if (smem > smem_max) {                      // rows too long to stage: unstaged variant (row_ptr windows only)
+            flavour = -1;
+            p.cap = 0;
+            p.stages = user_stages ? (uint32_t)std::min(tn.stages, 8) : 3u;
+            smem = row_kernel_smem_bytes(m.dtype, p, nw);
+        }
+        if (smem > smem_max) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: slice ring does not fit shared memory");
+
+        p.P = pick_rows_per_warp(m, dev, tn, sh, p.R, nw, resident);
+        const uint64_t S = (uint64_t)nw * p.P;
+        out->sh = sh;
+        out->grouped = grouped;
+        out->flavour = flavour;
+        out->nw = nw;
+        out->R = p.R;
+        out->P = p.P;
+        out->stages = p.stages;
+        out->cap = p.cap;
+        out->num_super = (uint32_t)((m.rows + S - 1) / S);
+        out->smem = smem;
+        out->resident = resident;
+        return BSM_OK;
+    }
 }
 
 static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags,
@@ -483,10 +611,9 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
     uint32_t tile = tn.col_tile > 0 ? (uint32_t)tn.col_tile : n_total;
     tile = std::min<uint32_t>(tile, 32u * vmax * 4u);   // widest shape one pass can hold in registers
     if (tile < n_total && tile % vmax) tile = std::max<uint32_t>(vmax, tile / vmax * vmax);
-    const double mean = mean_row_nnz(a);
     const bool multi = scatter && scatter->n_peers > 0;
-    const bool user_R = tn.rows_per_slice > 0, user_nw = tn.warps_per_cta > 0, user_stages = tn.stages > 0;
-    const size_t smem_max = (size_t)g_rt.max_smem_optin - 1024;
+    const MatrixFacts m = facts_of(a);
+    const DeviceFacts dev{g_rt.sm_count, (size_t)g_rt.max_smem_optin - 1024};
     int passes = 0;
     g_info = bsm_launch_info();
     g_info.algo = BSM_ALGO_VECTOR;
@@ -509,83 +636,17 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             p.n_peers = (uint32_t)scatter->n_peers;
             for (int d = 0; d < scatter->n_peers; ++d) p.peers[d] = (char *)scatter->peer_data[d] + c_off;
         }
-        // second attempt = without grouped lanes, when their (always staged) slices do not fit shared memory
-        for (bool allow_grouped = true;; allow_grouped = false) {
-            Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows != 0);
-            bool grouped_by_default = false;
-            const bool grouped = regroup_lanes(a, tn, n, s, allow_grouped && !scatter, sh, grouped_by_default);
-            const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
-            const uint32_t rpp = 32u / (uint32_t)sh.G;   // rows side by side in one warp
-            const uint32_t rq = std::max(4u, rpp);       // slice granularity (rpp is a power of two)
-
-            // rows per TMA slice: ~128 entries per bulk copy (~224 with one register tile per lane, r1_sweepi_*, and for
-            // 8 lanes x 2 tiles); narrow shapes want several row passes per slice to amortise the slice bookkeeping
-            uint32_t R;
-            if (user_R) {
-                R = (uint32_t)tn.rows_per_slice;
-            } else {
-                const double target = ((sh.G == 32 && sh.NT == 1) || (grouped && grouped_by_default && sh.NT == 2)) ? 224.0 : 128.0;
-                R = (uint32_t)std::min<double>(256.0, std::max(1.0, target / std::max(1.0, mean)));
-                if (sh.G < 32) R = std::max(R, 4u * rpp);
-            }
-            R = std::max(rq, R / rq * rq);
-            // a stencil-like matrix: the slice must divide the line length, or the rows per warp (a multiple of the
-            // slice) stop matching the lines and the L1 sharing between the warps of a CTA is lost (measured on a
-            // 5-entry-per-row stencil, line 256: 24-row slices -> P = 264: 12.9 ms; 16-row slices -> P = 256: see
-            // profiles/r1_probe_near_diag.jsonl)
-            if (!user_R && a->row_stride >= 2 * rq && a->row_stride % R) {
-                uint32_t r2 = R;
-                while (r2 > rq && a->row_stride % r2) r2 -= rq;
-                if (a->row_stride % r2 == 0) R = r2;
-            }
-
-            int flavour = pick_row_flavour(tn, sh, wide_full, grouped, grouped_by_default, multi);
-            // warps per CTA: what the flavour was compiled for; fewer on small matrices, so that no SM idles behind a
-            // handful of fat super-batches
-            const bool big_cta = (wide_full && (flavour == 5 || flavour == 6 || flavour == 7)) || (grouped && flavour == 6);
-            const int max_warps = big_cta ? 24 : ((flavour >= 2 && (wide_full || grouped)) ? 8 : 16);
-            int nw = user_nw ? std::min(tn.warps_per_cta, 24) : (big_cta ? 24 : 16);
-            if (!user_nw) {
-                const uint64_t rows_per_warp_min = big_cta ? R : rq;
-                const int nw_floor = big_cta ? 3 : 2;
-                while (nw > nw_floor && (uint64_t)nw * rows_per_warp_min * (uint64_t)g_rt.sm_count > a->rows) nw /= 2;
-            }
-            nw = std::min(nw, max_warps);
-
-            // The stage must hold the entries of ANY R consecutive rows (+3 for the 16-byte aligned start, + slack: the
-            // vectorised A-stream reads run up to two gather windows past the slice). Shrink, in this order, the ring
-            // depth, the slice and the CTA until the rings fit: first under a soft limit that leaves most of the 228 KB
-            // to L1 (where wide B rows live), then under the hardware limit. If even the smallest slice cannot be
-            // staged, col_idx / values are read from global memory instead (unstaged variant).
-            const int resident = ((wide_full || grouped) && (flavour == 2 || flavour == 4)) ? 3 : 1;   // CTAs per SM the flavour targets
-            const size_t smem_soft = (size_t)n * s <= 64 ? smem_max : std::min<size_t>(smem_max, (160 * 1024) / resident);
-            const uint32_t window = flavour == 7 ? 10u : (sh.NT >= 4 ? 2u : (sh.NT == 2 ? 4u : 8u)) * (flavour == 1 ? 2u : 1u);   // gathers in flight
-            const uint32_t r_floor = sh.G < 32 ? std::max(rq, 2u * rpp) : rq;
-            p.R = R;
-            p.stages = user_stages ? (uint32_t)std::min(tn.stages, 8) : (grouped && grouped_by_default && sh.G >= 8 ? 2u : 3u);
-            auto smem_now = [&]() {
-                p.cap = (uint32_t)pad4((uint64_t)p.R * a->max_row_nnz + 3) + 2 * window + 4;
-                return row_kernel_smem_bytes(a->dtype, p, nw);
-            };
-            size_t smem = smem_now();
-            while (smem > smem_soft && p.stages > 2 && !user_stages) { --p.stages; smem = smem_now(); }
-            while (smem > smem_soft && p.R > r_floor && !user_R) { p.R = std::max(r_floor, p.R / 2 / rq * rq); smem = smem_now(); }
-            while (smem > smem_soft && nw > 8 && !user_nw) { nw /= 2; smem = smem_now(); }
-            while (smem > smem_max && p.stages > 1) { --p.stages; smem = smem_now(); }
-            while (smem > smem_max && p.R > rq && !user_R) { p.R = std::max(rq, p.R / 2 / rq * rq); smem = smem_now(); }
-            while (smem > smem_max && nw > 2 && !user_nw) { nw /= 2; smem = smem_now(); }
-            if (smem > smem_max && grouped) continue;   // the grouped shapes have no unstaged variant: a warp per row instead
-            if (smem > smem_max) {                      // rows too long to stage: unstaged variant (row_ptr windows only)
-                flavour = -1;
-                p.cap = 0;
-                p.stages = user_stages ? (uint32_t)std::min(tn.stages, 8) : 3u;
-                smem = row_kernel_smem_bytes(a->dtype, p, nw);
-            }
-            if (smem > smem_max) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_vector: slice ring does not fit shared memory");
-
-            p.P = pick_rows_per_warp(a, tn, sh, p.R, nw, resident);
-            const uint64_t S = (uint64_t)nw * p.P;
-            p.num_super = (uint32_t)((a->rows + S - 1) / S);
+        VectorPlan plan;
+        BSM_TRY(plan_vector_pass(m, dev, tn, n, PassAlign{b->ld, c->ld, col0, b->data, c->data}, scatter != nullptr, multi, &plan));
+        const Shape sh = plan.sh;
+        const int flavour = plan.flavour, nw = plan.nw;
+        const size_t smem = plan.smem;
+        p.R = plan.R;
+        p.P = plan.P;
+        p.stages = plan.stages;
+        p.cap = plan.cap;
+        p.num_super = plan.num_super;
+        {
             const int block = nw * 32;
             int occ = 0;
             BSM_TRY(row_kernel_occupancy(a->dtype, sh, n, flavour, multi, block, smem, &occ));
@@ -605,7 +666,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             g_info.reg_flavour = flavour + 1;
             g_info.stages = (int)p.stages;
             g_info.capacity = (int)p.cap;
-            break;
         }
     }
     g_info.passes = passes;
@@ -1491,6 +1551,48 @@ int bsm_last_launch_info(bsm_launch_info *info)
     return BSM_OK;
 }
 uint64_t bsm_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// Dry run of the vector kernel's launch heuristics — pure host arithmetic, no device needed (the CPU test-suite pins
+// the heuristics with it). Operands are assumed 16-byte aligned with ld = n rounded up to 16 bytes; `grid` assumes the
+// occupancy the chosen flavour targets.
+int bsm_plan_vector(int dtype, uint64_t rows, uint64_t nnz, uint64_t max_row_nnz, uint32_t row_stride, uint64_t n_cols,
+                    const bsm_tuning *tuning, int sm_count, uint64_t smem_optin_bytes, bsm_launch_info *out)
+{
+    if (!out) return fail(BSM_ERR_INVALID_ARGUMENT, "plan_vector: null out");
+    if (dtype != BSM_F32 && dtype != BSM_F64) return fail(BSM_ERR_DTYPE_MISMATCH, "plan_vector: dtype must be f32 or f64");
+    if (sm_count <= 0 || smem_optin_bytes < 2048 || n_cols == 0 || n_cols >= 0xFFFFFFF0ull)
+        return fail(BSM_ERR_INVALID_ARGUMENT, "plan_vector: bad device facts or column count");
+    bsm_tuning tn{};
+    if (tuning) tn = *tuning;
+    const size_t s = dtype_size(dtype);
+    const int vmax = (int)(16 / s);
+    const uint32_t n_total = (uint32_t)n_cols;
+    uint32_t tile = tn.col_tile > 0 ? (uint32_t)tn.col_tile : n_total;
+    tile = std::min<uint32_t>(tile, 32u * vmax * 4u);
+    if (tile < n_total && tile % vmax) tile = std::max<uint32_t>(vmax, tile / vmax * vmax);
+    const uint32_t n = std::min(tile, n_total);
+    const MatrixFacts m{dtype, rows, nnz, max_row_nnz, row_stride};
+    const DeviceFacts dev{sm_count, (size_t)smem_optin_bytes - 1024};
+    const uint64_t ld = round_up(n_total, vmax);
+    VectorPlan plan;
+    BSM_TRY(plan_vector_pass(m, dev, tn, n, PassAlign{ld, ld, 0, nullptr, nullptr}, false, false, &plan));
+    *out = bsm_launch_info();
+    out->algo = BSM_ALGO_VECTOR;
+    out->vec_elems = plan.sh.V;
+    out->lanes_per_row = plan.sh.G;
+    out->reg_tiles = plan.sh.NT;
+    out->block = plan.nw * 32;
+    out->grid = (int)std::min<uint64_t>(plan.num_super, (uint64_t)sm_count * plan.resident);
+    out->smem_bytes = (int)plan.smem;
+    out->rows_per_slice = (int)plan.R;
+    out->rows_per_warp = (int)plan.P;
+    out->stages = (int)plan.stages;
+    out->capacity = (int)plan.cap;
+    out->reg_flavour = plan.flavour + 1;
+    out->col_tile = (int)tile;
+    out->passes = (int)((n_total + tile - 1) / tile);
+    return BSM_OK;
+}
 
 int bsm_dense_residual_norm(const bsm_dense *ax, const bsm_dense *b, double *resid_fro, double *b_fro)
 {

@@ -198,6 +198,11 @@ int bsm_dense_upload_rowmajor(int dtype, uint64_t rows, uint64_t cols, const voi
 int bsm_spmm(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, int algo);
 int bsm_spmm_tuned(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning *tuning);
 int bsm_last_launch_info(bsm_launch_info *info);
+/* Dry run of the vector kernel's launch heuristics for a matrix described by its statistics (row_stride = line length
+ * of a stencil-like matrix, 0 = none) on a device described by its SM count and opt-in shared memory per CTA.
+ * Pure host arithmetic: needs no device. Operands are assumed 16-byte aligned. */
+int bsm_plan_vector(int dtype, uint64_t rows, uint64_t nnz, uint64_t max_row_nnz, uint32_t row_stride, uint64_t n_cols,
+                    const bsm_tuning *tuning, int sm_count, uint64_t smem_optin_bytes, bsm_launch_info *out);
 /* cumulative number of this library's kernels launched by this process (bench "gpu_launches") */
 uint64_t bsm_kernel_launch_count(void);
 

@@ -1,0 +1,93 @@
+"""CPU: the launch heuristics of the vector kernel, through bsm_plan_vector (a dry run: no device needed).
+
+Every expectation below is a configuration that was MEASURED on a B200 this round (profiles/README.md); the
+tests pin the plan, so that a later change to the heuristics that silently reverts one of them fails here
+rather than in a benchmark. B200: 148 SMs, 227 KB opt-in shared memory per CTA."""
+import ctypes as C
+
+import pytest
+
+from basic_sparse_matrix_b200 import _lib
+
+SMS, SMEM = 148, 232448
+F32, F64 = _lib.dtype_code("float32"), _lib.dtype_code("float64")
+
+
+def plan(dtype, rows, nnz, max_row, stride, n, **tune):
+    t = _lib.Tuning()
+    for k, v in tune.items():
+        setattr(t, k, v)
+    info = _lib.LaunchInfo()
+    st = _lib.lib().bsm_plan_vector(dtype, rows, nnz, max_row, stride, n, C.byref(t), SMS, SMEM, C.byref(info))
+    assert st == 0, _lib.lib().bsm_last_error_string()
+    return info.as_dict()
+
+
+L3D = dict(rows=256 ** 3, nnz=117_047_296, max_row=7)          # 3-D 7-point Laplacian 256^3
+
+
+def test_headline_x128_f64():
+    p = plan(F64, L3D["rows"], L3D["nnz"], L3D["max_row"], 256, 128)
+    assert (p["lanes_per_row"], p["reg_tiles"], p["vec_elems"]) == (32, 2, 2)
+    assert (p["block"], p["grid"]) == (256, 3 * SMS)            # 3 CTAs x 8 warps per SM
+    assert (p["rows_per_slice"], p["rows_per_warp"], p["stages"]) == (16, 256, 3)
+    assert p["reg_flavour"] == 5
+
+
+def test_north_star_x64_f64_uses_grouped_lanes():
+    p = plan(F64, L3D["rows"], L3D["nnz"], L3D["max_row"], 256, 64)
+    assert (p["lanes_per_row"], p["reg_tiles"]) == (8, 4)        # four rows per warp side by side
+    assert (p["block"], p["grid"]) == (768, SMS)                 # one CTA of 24 warps per SM
+    assert (p["rows_per_slice"], p["rows_per_warp"], p["stages"]) == (16, 256, 2)
+    # uneven rows (hub rows) stay on the warp-per-row stream
+    q = plan(F64, L3D["rows"], L3D["nnz"], 60, 0, 64)
+    assert (q["lanes_per_row"], q["reg_tiles"]) == (32, 1)
+
+
+@pytest.mark.parametrize("dtype,n,lanes,tiles", [(F64, 32, 8, 2), (F32, 64, 8, 2), (F64, 16, 4, 2), (F32, 128, 8, 4)])
+def test_narrow_rows_are_grouped_on_short_regular_rows(dtype, n, lanes, tiles):
+    p = plan(dtype, L3D["rows"], L3D["nnz"], L3D["max_row"], 256, n)
+    assert (p["lanes_per_row"], p["reg_tiles"]) == (lanes, tiles)
+    assert p["rows_per_warp"] == 256
+
+
+def test_long_rows_stay_row_by_row_on_narrow_shapes():
+    # band, half-bandwidth 32, x 32 f32 (when the row-block kernel is not used): 8 lanes, one tile, row by row
+    p = plan(F32, 1 << 20, 68_156_384, 65, 0, 32)
+    assert (p["lanes_per_row"], p["reg_tiles"]) == (8, 1)
+
+
+def test_spmv_is_a_row_per_lane():
+    p = plan(F64, 2048 ** 2, 20_963_328, 5, 2048, 1)
+    assert (p["lanes_per_row"], p["reg_tiles"], p["vec_elems"]) == (1, 1, 1)
+
+
+@pytest.mark.parametrize("line,want_slice", [(256, 16), (252, 12), (4096, 16), (250, 16), (100, 16)])
+def test_rows_per_warp_follow_the_line_length_whatever_it_is(line, want_slice):
+    """252: the slice is cut to a divisor of the line; 250 (no multiple of 4 divides it): short last slice, P = 250.
+    A slice that does not divide the line used to push P to the next multiple (4096 -> 4104) and cost 60 %."""
+    rows = line ** 3 if line <= 256 else line ** 2
+    mean = 7 if line <= 256 else 5
+    p = plan(F64, rows, rows * mean, mean, line, 128)
+    assert p["rows_per_warp"] in (line, line // 2, line // 4), p
+    assert line % p["rows_per_warp"] == 0
+    assert p["rows_per_slice"] == want_slice, p
+
+
+def test_small_row_blocks_trade_line_length_for_balance():
+    # a 1/8 row block of the headline matrix: half a line per warp loses less to wave quantisation
+    p = plan(F64, L3D["rows"] // 8, L3D["nnz"] // 8, 7, 256, 128)
+    assert p["rows_per_warp"] == 128
+
+
+def test_tuning_overrides_and_slices_that_do_not_fit():
+    p = plan(F64, L3D["rows"], L3D["nnz"], 7, 256, 128, rows_per_slice=32, stages=2, rows_per_warp=96, warps_per_cta=4)
+    assert (p["rows_per_slice"], p["stages"], p["rows_per_warp"], p["block"]) == (32, 2, 96, 128)
+    # rows too long for any stage: the unstaged variant (capacity 0), never the grouped shapes
+    q = plan(F64, 100_000, 100_000 * 50, 40_000, 0, 64)
+    assert q["capacity"] == 0 and q["reg_flavour"] == 0 and (q["lanes_per_row"], q["reg_tiles"]) == (32, 1)
+
+
+def test_few_rows_shrink_the_cta():
+    p = plan(F64, 20_000, 140_000, 7, 0, 64)
+    assert p["block"] < 768 and p["grid"] >= 100
