@@ -131,6 +131,7 @@ def _declare(L):
     sig("bsm_spmm", i32, vp, vp, vp, i32)
     sig("bsm_spmm_tuned", i32, vp, vp, vp, C.POINTER(Tuning))
     sig("bsm_last_launch_info", i32, C.POINTER(LaunchInfo))
+    sig("bsm_line_length_of_row", C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, u64)
     sig("bsm_plan_vector", i32, i32, u64, u64, u64, C.c_uint32, u64, C.POINTER(Tuning), i32, u64, C.POINTER(LaunchInfo))
     sig("bsm_kernel_launch_count", u64)
     sig("bsm_dense_to_csr", i32, vp, PV)

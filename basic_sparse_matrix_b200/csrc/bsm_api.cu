@@ -111,6 +111,27 @@ static int alloc_csr(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, bsm_
 // consecutive rows one warp should own so that the warps of a CTA sweep adjacent grid lines and
 // share those B rows through L1. Sampled from three interior rows; 0 when the matrix is not of that
 // shape. A performance hint only: any value is correct.
+// Line length seen from one row: the smallest distance > 1 of a stored column from the diagonal (NOT from the row's
+// median column: on a grid boundary row the median is a neighbour and the result is off by one — 4095 for a line of
+// 4096). A box stencil (9- / 27-point) also stores the neighbours of its line neighbour — distances nx-1, nx, nx+1 —
+// and yields nx. 0 when the row has no such column. Pure host arithmetic (bsm_line_length_of_row, CPU-tested).
+static uint32_t line_length_of_row(const uint32_t *cols, uint32_t len, uint64_t diag)
+{
+    auto dist = [&](uint32_t i) { return cols[i] > diag ? cols[i] - diag : diag - cols[i]; };
+    uint64_t stride = 0;
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint64_t d = dist(i);
+        if (d > 1 && (stride == 0 || d < stride)) stride = d;
+    }
+    if (stride == 0 || stride > 0xFFFFFFF0ull) return 0;
+    bool plus1 = false, plus2 = false;
+    for (uint32_t i = 0; i < len; ++i) {
+        plus1 |= dist(i) == stride + 1;
+        plus2 |= dist(i) == stride + 2;
+    }
+    return (uint32_t)(plus1 && plus2 ? stride + 1 : stride);
+}
+
 static int detect_row_stride(bsm_csr *a)
 {
     a->row_stride = 0;
@@ -126,23 +147,7 @@ static int detect_row_stride(bsm_csr *a)
         uint32_t cols[64];
         BSM_CUDA(cudaMemcpyAsync(cols, a->col_idx + rp[0], len * 4, cudaMemcpyDeviceToHost, g_rt.stream));
         BSM_CUDA(cudaStreamSynchronize(g_rt.stream));
-        // smallest distance > 1 of a stored column from the diagonal (NOT from the row's median column: on a grid
-        // boundary row the median is a neighbour and the result is off by one — 4095 for a line of 4096)
-        const uint64_t diag = r + a->row_offset;
-        uint32_t stride = 0;
-        for (uint32_t i = 0; i < len; ++i) {
-            const uint64_t d64 = cols[i] > diag ? cols[i] - diag : diag - cols[i];
-            const uint32_t d = (uint32_t)std::min<uint64_t>(d64, 0xFFFFFFFFull);
-            if (d > 1 && (stride == 0 || d < stride)) stride = d;
-        }
-        // a box stencil (9- / 27-point) also stores the neighbours of the line neighbour: distances nx-1, nx, nx+1 -> nx
-        bool plus1 = false, plus2 = false;
-        for (uint32_t i = 0; i < len && stride; ++i) {
-            const uint64_t d64 = cols[i] > diag ? cols[i] - diag : diag - cols[i];
-            plus1 |= d64 == (uint64_t)stride + 1;
-            plus2 |= d64 == (uint64_t)stride + 2;
-        }
-        if (plus1 && plus2) stride += 1;
+        const uint32_t stride = line_length_of_row(cols, len, r + a->row_offset);
         if (stride < 16 || stride > 16384 || (found && stride != found)) return BSM_OK;
         found = stride;
     }
@@ -1551,6 +1556,8 @@ int bsm_last_launch_info(bsm_launch_info *info)
     return BSM_OK;
 }
 uint64_t bsm_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+uint32_t bsm_line_length_of_row(const uint32_t *cols, uint32_t len, uint64_t diag) { return cols && len ? line_length_of_row(cols, len, diag) : 0u; }
 
 // Dry run of the vector kernel's launch heuristics — pure host arithmetic, no device needed (the CPU test-suite pins
 // the heuristics with it). Operands are assumed 16-byte aligned with ld = n rounded up to 16 bytes; `grid` assumes the

@@ -201,6 +201,9 @@ int bsm_last_launch_info(bsm_launch_info *info);
 /* Dry run of the vector kernel's launch heuristics for a matrix described by its statistics (row_stride = line length
  * of a stencil-like matrix, 0 = none) on a device described by its SM count and opt-in shared memory per CTA.
  * Pure host arithmetic: needs no device. Operands are assumed 16-byte aligned. */
+/* The stencil line length one row suggests (what the upload samples from three rows to set `row_stride`): the smallest
+ * distance > 1 of a stored column from the diagonal `diag`; nx for a box stencil storing nx-1, nx, nx+1. Pure host. */
+uint32_t bsm_line_length_of_row(const uint32_t *cols, uint32_t len, uint64_t diag);
 int bsm_plan_vector(int dtype, uint64_t rows, uint64_t nnz, uint64_t max_row_nnz, uint32_t row_stride, uint64_t n_cols,
                     const bsm_tuning *tuning, int sm_count, uint64_t smem_optin_bytes, bsm_launch_info *out);
 /* cumulative number of this library's kernels launched by this process (bench "gpu_launches") */

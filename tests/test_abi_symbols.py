@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     hdr = open(os.path.join(ROOT, "include", "bsm.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)          # strip comments
-    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|uint64_t|char)\s*\*?\s*(bsm_[a-z0-9_]+)\s*\(", hdr, flags=re.M)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|uint64_t|uint32_t|char)\s*\*?\s*(bsm_[a-z0-9_]+)\s*\(", hdr, flags=re.M)
     return sorted(set(names))
 
 

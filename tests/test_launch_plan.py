@@ -91,3 +91,24 @@ def test_tuning_overrides_and_slices_that_do_not_fit():
 def test_few_rows_shrink_the_cta():
     p = plan(F64, 20_000, 140_000, 7, 0, 64)
     assert p["block"] < 768 and p["grid"] >= 100
+
+
+def line_length(cols, diag):
+    arr = (C.c_uint32 * len(cols))(*cols)
+    return _lib.lib().bsm_line_length_of_row(arr, len(cols), diag)
+
+
+def test_line_length_from_a_row():
+    nx, i = 4096, 4096 * 1000
+    assert line_length([i - nx, i - 1, i, i + 1, i + nx], i) == nx            # interior row of a 5-point stencil
+    assert line_length([i - nx, i, i + 1, i + nx], i) == nx                   # x = 0 boundary row (the median column is i + 1)
+    assert line_length([i - nx, i - 1, i, i + nx], i) == nx                   # x = nx - 1 boundary row
+    assert line_length([i, i + 1, i + nx], i) == nx                           # first line
+    p = 256
+    j = 65536 * 100 + 256 * 7
+    assert line_length([j - p * p, j - p, j, j + 1, j + p, j + p * p], j) == p  # 7-point, x = 0
+    box = [j + dz * p * p + dy * p + dx for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    assert line_length(sorted(box), j) == p                                   # 27-point: distances p-1, p, p+1 -> p
+    assert line_length([j - 1, j, j + 1], j) == 0                             # tridiagonal: no line
+    # row blocks of a partitioned matrix keep global columns: the diagonal is local row + row offset
+    assert line_length([i - nx, i - 1, i, i + 1, i + nx], (i - 12345) + 12345) == nx
