@@ -383,6 +383,20 @@ static Shape pick_shape(uint32_t n, uint64_t ldb, uint64_t ldc, uint64_t col0, c
     return sh;
 }
 
+// Columns one pass can take starting at col0 when `want` remain (<= the tile): the lane shape holds at most
+// G * V * NT columns, and alignment can force vectors narrower than 16 bytes — 129 f32 columns are 129 one-element
+// lanes, more than the 128 that four register tiles hold. Then the pass is cut to a width the widest vectors divide
+// (128 of the 129; the last column goes to the next pass), or failing that to what the narrow vectors hold.
+template <typename ShapeOf> static uint32_t fit_pass_width(uint32_t want, int vmax, ShapeOf &&shape_of)
+{
+    auto holds = [](const Shape &x) { return (uint32_t)(x.G * x.V * x.NT); };
+    const Shape sh = shape_of(want);
+    if (holds(sh) >= want) return want;
+    const uint32_t even = want / (uint32_t)vmax * (uint32_t)vmax;
+    if (even >= (uint32_t)vmax && even < want && holds(shape_of(even)) >= even) return even;
+    return holds(sh);
+}
+
 // Geometry of the vector kernel for one column pass (see spmm_rows.cu).
 // Scatter variant of the vector kernel: C is this rank's FULL result buffer, the rank's rows start at
 // row_offset, and every row is also stored to `n_peers` further full buffers (peer GPUs over NVLink).
@@ -623,8 +637,9 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
     g_info = bsm_launch_info();
     g_info.algo = BSM_ALGO_VECTOR;
     g_info.col_tile = (int)tile;
-    for (uint32_t col0 = 0; col0 < n_total; col0 += tile, ++passes) {
-        const uint32_t n = std::min(tile, n_total - col0);
+    for (uint32_t col0 = 0, n = 0; col0 < n_total; col0 += n, ++passes) {
+        n = fit_pass_width(std::min(tile, n_total - col0), vmax,
+                           [&](uint32_t w) { return pick_shape(w, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows != 0); });
         const size_t c_off = ((scatter ? (size_t)scatter->row_offset * c->ld : 0) + (size_t)col0) * s;
         RowParams p{};
         p.row_ptr = a->row_ptr;
@@ -712,8 +727,10 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
     g_info = bsm_launch_info();
     g_info.algo = BSM_ALGO_MERGE;
     int passes = 0;
-    for (uint32_t col0 = 0; col0 < n_total; col0 += tile, ++passes) {
-        const uint32_t n = std::min(tile, n_total - col0);
+    for (uint32_t col0 = 0, n = 0; col0 < n_total; col0 += n, ++passes) {
+        n = fit_pass_width(std::min(tile, n_total - col0), vmax, [&](uint32_t w) {
+            return pick_shape(w, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows >= 0, round_up(w, vmax));
+        });
         const uint64_t ldcar = round_up(n, vmax);
         Shape sh = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, tn.prefer_wide_rows >= 0, ldcar);
         // fewer lanes per chunk, 2 or 4 register tiles per lane (128-bit lanes, full-width shapes): one LDS.128 of the
@@ -1577,12 +1594,19 @@ int bsm_plan_vector(int dtype, uint64_t rows, uint64_t nnz, uint64_t max_row_nnz
     uint32_t tile = tn.col_tile > 0 ? (uint32_t)tn.col_tile : n_total;
     tile = std::min<uint32_t>(tile, 32u * vmax * 4u);
     if (tile < n_total && tile % vmax) tile = std::max<uint32_t>(vmax, tile / vmax * vmax);
-    const uint32_t n = std::min(tile, n_total);
     const MatrixFacts m{dtype, rows, nnz, max_row_nnz, row_stride};
     const DeviceFacts dev{sm_count, (size_t)smem_optin_bytes - 1024};
     const uint64_t ld = round_up(n_total, vmax);
+    // the plan reported is that of the FIRST pass; `passes` counts them all, `capacity`... see bsm_launch_info
+    uint32_t first_n = 0;
+    int passes = 0;
+    for (uint32_t col0 = 0, n = 0; col0 < n_total; col0 += n, ++passes) {
+        n = fit_pass_width(std::min(tile, n_total - col0), vmax, [&](uint32_t w) { return pick_shape(w, ld, ld, col0, nullptr, nullptr, s, tn.prefer_wide_rows != 0); });
+        if (n == 0) return fail(BSM_ERR_INVALID_ARGUMENT, "plan_vector: empty pass");
+        if (!first_n) first_n = n;
+    }
     VectorPlan plan;
-    BSM_TRY(plan_vector_pass(m, dev, tn, n, PassAlign{ld, ld, 0, nullptr, nullptr}, false, false, &plan));
+    BSM_TRY(plan_vector_pass(m, dev, tn, first_n, PassAlign{ld, ld, 0, nullptr, nullptr}, false, false, &plan));
     *out = bsm_launch_info();
     out->algo = BSM_ALGO_VECTOR;
     out->vec_elems = plan.sh.V;
@@ -1596,8 +1620,8 @@ int bsm_plan_vector(int dtype, uint64_t rows, uint64_t nnz, uint64_t max_row_nnz
     out->stages = (int)plan.stages;
     out->capacity = (int)plan.cap;
     out->reg_flavour = plan.flavour + 1;
-    out->col_tile = (int)tile;
-    out->passes = (int)((n_total + tile - 1) / tile);
+    out->col_tile = (int)first_n;   // width of the first pass
+    out->passes = passes;
     return BSM_OK;
 }
 

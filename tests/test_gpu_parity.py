@@ -545,3 +545,23 @@ def test_borrowed_strided_operands(gpu, dtype, algo):
         for h in (bv, cv, bd, cd):
             h.close()
     a.close()
+
+
+# (last in the file: first exercised on a GPU by the round-end run)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_odd_wide_column_counts(gpu, dtype):
+    """n = 129, 131, 255, 257: alignment forces one-element lanes, more of them than one pass holds; the pass is split
+    (fit_pass_width) instead of dropping the columns past 32 lanes x 4 tiles. Every kernel family."""
+    rng = np.random.default_rng(515)
+    m, k = 700, 300
+    v, ci, ri = random_csr(rng, m, k, dtype, mean_len=6, giant_row=5, giant_len=900, exact=True)
+    vb, cb, rb = _runs_csr(rng, m, k, dtype, 40)
+    for n in (129, 131, 255, 257):
+        b = random_dense(rng, k, n, dtype, exact=True)
+        want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+        for algo in ("vector", "merge", "auto"):
+            got, info = gpu_product(gpu, (m, k), v, ci, ri, b, algo)
+            assert info["passes"] >= 2
+            assert_bitwise(got, want, f"n={n} {algo}")
+        got, _ = gpu_product(gpu, (m, k), vb, cb, rb, b, "rowblock")
+        assert_bitwise(got, ref_numpy.mul_dense_rowmajor(vb, cb, rb, b), f"n={n} rowblock")

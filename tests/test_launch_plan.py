@@ -112,3 +112,63 @@ def test_line_length_from_a_row():
     assert line_length([j - 1, j, j + 1], j) == 0                             # tridiagonal: no line
     # row blocks of a partitioned matrix keep global columns: the diagonal is local row + row offset
     assert line_length([i - nx, i - 1, i, i + 1, i + nx], (i - 12345) + 12345) == nx
+
+
+# ---- invariants of every plan (what launch_spmm_rows and the kernel rely on), over random inputs ---------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=400, deadline=None)
+@given(dtype=st.sampled_from([F32, F64]),
+       rows=st.integers(1, 1 << 26),
+       mean=st.floats(0.1, 300.0),
+       spread=st.floats(1.0, 60.0),
+       stride=st.sampled_from([0, 0, 16, 37, 50, 100, 250, 252, 256, 1000, 4096, 16384]),
+       n=st.integers(1, 600),
+       tune=st.fixed_dictionaries({}, optional={
+           "rows_per_slice": st.sampled_from([4, 8, 12, 16, 32, 64, 256]), "stages": st.integers(1, 8),
+           "warps_per_cta": st.sampled_from([1, 2, 3, 4, 8, 16, 24]), "rows_per_warp": st.sampled_from([4, 16, 33, 50, 128, 251, 512]),
+           "reg_flavour": st.integers(1, 8), "lanes_per_row": st.sampled_from([4, 8, 16, 32]), "prefer_wide_rows": st.sampled_from([0, 1]),
+           "col_tile": st.sampled_from([8, 16, 32, 64, 128])}))
+def test_every_plan_is_launchable(dtype, rows, mean, spread, stride, n, tune):
+    nnz = max(1, min(int(rows * mean), (1 << 32) - 64))
+    max_row = max(1, min(int(max(mean, 1.0) * spread) + 1, nnz))
+    t = _lib.Tuning()
+    for k, v in tune.items():
+        setattr(t, k, v)
+    info = _lib.LaunchInfo()
+    status = _lib.lib().bsm_plan_vector(dtype, rows, nnz, max_row, stride, n, C.byref(t), SMS, SMEM, C.byref(info))
+    if status != 0:                                    # only one legitimate refusal: a user-fixed slice that cannot fit
+        assert b"does not fit shared memory" in _lib.lib().bsm_last_error_string() and "rows_per_slice" in tune
+        return
+    p = info.as_dict()
+    s = 4 if dtype == F32 else 8
+    G, NT, V, R, P = p["lanes_per_row"], p["reg_tiles"], p["vec_elems"], p["rows_per_slice"], p["rows_per_warp"]
+    assert G in (1, 2, 4, 8, 16, 32) and NT in (1, 2, 4) and V * s <= 16 and V >= 1
+    width = min(n, p["col_tile"])
+    assert G * NT * V >= width                          # one pass covers its columns
+    assert R >= 4 and R % 4 == 0 and R % max(1, 32 // G) == 0
+    assert P >= R
+    if not (G == 32 or NT > 1):
+        assert P % R == 0                               # the row-by-row shapes need whole slices
+    assert 32 <= p["block"] <= 768 and p["block"] % 32 == 0
+    assert 1 <= p["stages"] <= 8
+    assert p["smem_bytes"] <= SMEM - 1024
+    if p["capacity"]:                                   # staged: any R consecutive rows fit (+ aligned start)
+        assert p["capacity"] % 4 == 0 and p["capacity"] >= R * max_row + 3
+    else:
+        assert p["reg_flavour"] == 0                    # unstaged variant
+    warps = p["block"] // 32
+    supers = -(-rows // (warps * P))
+    assert 1 <= p["grid"] <= min(supers, 4 * SMS)
+    assert p["col_tile"] <= n and p["passes"] >= -(-n // p["col_tile"])   # col_tile = width of the first pass
+
+
+@pytest.mark.parametrize("dtype,n,first,passes", [(F32, 129, 128, 2), (F64, 129, 128, 2), (F64, 255, 254, 2), (F32, 258, 256, 2),
+                                                   (F32, 513, 512, 2), (F64, 300, 256, 2), (F32, 300, 300, 1), (F32, 130, 130, 1)])
+def test_pass_width_when_alignment_forces_narrow_vectors(dtype, n, first, passes):
+    """129 f32 columns are 129 one-element lanes — more than four register tiles of 32 lanes hold. The pass is cut to a
+    width the 16-byte vectors divide (128) and the rest goes to the next pass; before this the last column was dropped."""
+    p = plan(dtype, 1_000_000, 7_000_000, 7, 0, n)
+    assert (p["col_tile"], p["passes"]) == (first, passes)
+    assert p["lanes_per_row"] * p["reg_tiles"] * p["vec_elems"] >= first
