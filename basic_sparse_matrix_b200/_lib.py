@@ -35,6 +35,7 @@ ALGO_NAMES = {"auto": ALGO_AUTO, "vector": ALGO_VECTOR, "merge": ALGO_MERGE, "ro
 
 TUNE_A_EVICT_FIRST = 0x1
 TUNE_C_STREAMING = 0x2
+TUNE_FUSED = 0x4
 TUNE_LITERAL = 0x80000000
 
 
@@ -51,7 +52,8 @@ class Tuning(C.Structure):
         ("algo", C.c_int32), ("col_tile", C.c_int32), ("rows_per_slice", C.c_int32),
         ("stages", C.c_int32), ("warps_per_cta", C.c_int32), ("ctas_per_sm", C.c_int32),
         ("merge_items", C.c_int32), ("flags", C.c_uint32), ("rows_per_warp", C.c_int32),
-        ("prefer_wide_rows", C.c_int32), ("reg_flavour", C.c_int32), ("lanes_per_row", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("prefer_wide_rows", C.c_int32), ("reg_flavour", C.c_int32), ("lanes_per_row", C.c_int32), ("b_prefetch", C.c_int32),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -62,7 +64,7 @@ class LaunchInfo(C.Structure):
         ("block", C.c_int32), ("smem_bytes", C.c_int32), ("rows_per_slice", C.c_int32),
         ("stages", C.c_int32), ("capacity", C.c_int32), ("passes", C.c_int32),
         ("merge_items", C.c_int32), ("merge_chunks", C.c_int32), ("rows_per_warp", C.c_int32),
-        ("reg_flavour", C.c_int32), ("col_tile", C.c_int32), ("reserved", C.c_int32 * 1),
+        ("reg_flavour", C.c_int32), ("col_tile", C.c_int32), ("b_prefetch", C.c_int32),
     ]
 
     def as_dict(self):
@@ -116,6 +118,8 @@ def _declare(L):
         sig(f"bsm_mul_dense_host_{sfx}", i32, u64, u64, u64, vp, vp, vp, u64, u64, u64, vp, i32,
             C.POINTER(u64), PV, PV, PV)
         sig(f"bsm_mul_dense_host_dense_{sfx}", i32, u64, u64, u64, vp, vp, vp, u64, u64, u64, vp, vp, i32)
+        sig(f"bsm_mul_dense_host_into_{sfx}", i32, u64, u64, u64, vp, vp, vp, u64, u64, u64, vp, i32, u64, vp, vp, vp,
+            C.POINTER(u64))
         sig(f"bsm_mul_vector_{sfx}", i32, vp, vp, u64, vp, u64)
     sig("bsm_csr_from_device", i32, i32, u64, u64, u64, vp, vp, vp, i32, PV)
     sig("bsm_csr_free", i32, vp)
@@ -151,6 +155,9 @@ def _declare(L):
     sig("bsm_gen_band", i32, i32, u64, u64, u64, u64, PV)
     sig("bsm_gen_rmat", i32, i32, i32, u64, C.c_double, C.c_double, C.c_double, u64, i32, PV)
     sig("bsm_l2_flush", i32)
+    sig("bsm_phase_timers_enable", i32, i32)
+    sig("bsm_phase_timers_read", i32, C.POINTER(C.c_double), i32, i32)
+    sig("bsm_phase_name", C.c_char_p, i32)
 
 
 def lib() -> C.CDLL:

@@ -162,6 +162,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// L2 prefetch of a contiguous piece of global memory by the TMA unit (fire and forget; 16-byte aligned address and size)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // ---- per-lane column vectors -----------------------------------------------------------------
 template <typename T, int V> struct VecT;
 template <> struct VecT<double, 1> { using type = double; };
@@ -272,6 +278,32 @@ template <typename T, int V> __device__ __forceinline__ void axpy_unfused(T a, c
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = mul_add_unfused(a, b[i], acc[i]);
     }
+}
+// OPT-IN fused form (BSM_TUNE_FUSED): acc = fma(a, b, acc), one rounding per product-and-sum; f32 pairs on the packed pipe (FFMA2)
+template <typename T, int V> __device__ __forceinline__ void axpy_fused(T a, const T (&b)[V], T (&acc)[V])
+{
+    if constexpr (sizeof(T) == 4 && V % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < V; i += 2) {
+            unsigned long long aa, bb, cc;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[i]), "f"(b[i + 1]));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i]), "f"(acc[i + 1]));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i]), "=f"(acc[i + 1]) : "l"(cc));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = mul_add_fused(a, b[i], acc[i]);
+    }
+}
+template <bool FUSED, typename T, int V>
+__device__ __forceinline__ void axpy(T a, const T (&b)[V], T (&acc)[V], unsigned long long negzero2)
+{
+    if constexpr (FUSED)
+        axpy_fused<T, V>(a, b, acc);
+    else
+        axpy_unfused<T, V>(a, b, acc, negzero2);
 }
 // two -0.0f; `runtime_zero` must be 0 at run time and opaque at compile time (a kernel parameter bit that is never set)
 __device__ __forceinline__ unsigned long long packed_negzero(uint32_t runtime_zero)

@@ -87,13 +87,16 @@ int bsm_allgather_rows(bsm_comm *c, const bsm_dense *local_block, const uint64_t
         BSM_CUDA(cudaMemcpyAsync((char *)full->data + bounds[c->rank] * row_bytes, local_block->data, my_rows * row_bytes,
                                  cudaMemcpyDeviceToDevice, sm));
     BSM_NCCL(ncclGroupStart());
-    for (int root = 0; root < c->nranks; ++root) {
+    ncclResult_t res = ncclSuccess;
+    for (int root = 0; root < c->nranks && res == ncclSuccess; ++root) {
         const uint64_t r0 = bounds[root], r1 = bounds[root + 1];
         if (r1 == r0) continue;
         char *slot = (char *)full->data + r0 * row_bytes;
-        BSM_NCCL(ncclBroadcast(slot, slot, (r1 - r0) * row_bytes, ncclChar, root, c->comm, sm));
+        res = ncclBroadcast(slot, slot, (r1 - r0) * row_bytes, ncclChar, root, c->comm, sm);
     }
-    BSM_NCCL(ncclGroupEnd());
+    const ncclResult_t end = ncclGroupEnd();   // always close the group, also after a failed broadcast
+    if (res != ncclSuccess) return fail(BSM_ERR_NCCL, std::string("ncclBroadcast: ") + ncclGetErrorString(res));
+    if (end != ncclSuccess) return fail(BSM_ERR_NCCL, std::string("ncclGroupEnd: ") + ncclGetErrorString(end));
     return BSM_OK;
 }
 

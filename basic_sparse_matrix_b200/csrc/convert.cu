@@ -4,8 +4,11 @@
 //   * csr_row_stats (max row length -> kernel dispatch)
 //   * dense -> Csr zero-drop compaction: count -> scan -> scatter
 //     (result construction of mul_dense: sparse.rs:442 -> insert 222-233 -> finalise 206-219)
+#include <algorithm>
+
 #include "bsm_common.cuh"
 #include "kernels.h"
+#include "line_length.h"
 
 namespace bsm {
 
@@ -35,11 +38,14 @@ __global__ void fill_u32_kernel(uint32_t *dst, uint64_t count, uint32_t value)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) dst[i] = value;
 }
 
-static inline int grid_for(uint64_t count, int threads, int max_blocks = 148 * 16)
+// grid-stride launches: enough blocks to fill the device the runtime was initialised on (16 per SM)
+static inline int grid_for(uint64_t count, int threads)
 {
+    const int sms = rt().sm_count > 0 ? rt().sm_count : 148;
+    const uint64_t max_blocks = (uint64_t)sms * 16;
     uint64_t b = (count + threads - 1) / threads;
     if (b < 1) b = 1;
-    if (b > (uint64_t)max_blocks) b = max_blocks;
+    if (b > max_blocks) b = max_blocks;
     return (int)b;
 }
 
@@ -71,39 +77,20 @@ int launch_fill_u32(uint32_t *dst, uint64_t count, uint32_t value, cudaStream_t 
     return BSM_OK;
 }
 
-// ---- csr_row_stats ---------------------------------------------------------------------------
-__global__ void row_stats_kernel(const uint32_t *__restrict__ row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag)
+// ---- per-matrix statistics: ONE kernel, one readback ---------------------------------------------------------
+// stats[kStatMaxLen] longest row, [kStatBadRowPtr] row_ptr not non-decreasing / not ending at nnz / not starting at 0,
+// [kStatColMin/Max] smallest and largest stored column (which rows of B the matrix — or a rank's row block — reads),
+// [kStatVoters] rows of 3..64 entries, [kStatHist + s] how many of them suggest the stencil line length s
+// (line_length.h): the host takes the dominant one. Every row votes (warp-aggregated atomics), not a sample of three.
+__global__ void csr_stats_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col_idx, uint64_t rows, uint64_t nnz,
+                                 uint64_t row_offset, uint32_t *__restrict__ stats)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t m = 0;
-    bool bad = false;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += stride) {
-        const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
-        if (b < a)
-            bad = true;
-        else
-            m = max(m, b - a);
-    }
-    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_len, m);
-    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicExch(bad_flag, 1u);
-}
-
-int launch_row_stats(const uint32_t *row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag, cudaStream_t stream)
-{
-    if (rows == 0) return BSM_OK;
-    row_stats_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(row_ptr, rows, max_len, bad_flag);
-    BSM_CUDA(cudaGetLastError());
-    count_launch();
-    return BSM_OK;
-}
-
-// smallest / largest stored column index (which rows of B a matrix — or one rank's row block — reads)
-__global__ void col_range_kernel(const uint32_t *__restrict__ col_idx, uint64_t nnz, uint32_t *min_max)
-{
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    // entries: column range
     uint32_t lo = 0xFFFFFFFFu, hi = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    for (uint64_t i = tid; i < nnz; i += stride) {
         const uint32_t c = col_idx[i];
         lo = min(lo, c);
         hi = max(hi, c);
@@ -112,16 +99,46 @@ __global__ void col_range_kernel(const uint32_t *__restrict__ col_idx, uint64_t 
         lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
         hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(min_max, lo);
-        atomicMax(min_max + 1, hi);
+    if (lane == 0 && lo <= hi) {
+        atomicMin(stats + kStatColMin, lo);
+        atomicMax(stats + kStatColMax, hi);
     }
+    // rows: longest row, monotonicity, line-length votes
+    uint32_t m = 0;
+    bool bad = false;
+    if (tid == 0 && rows) bad = row_ptr[0] != 0u || row_ptr[rows] != (uint32_t)nnz;
+    const uint64_t rows_pad = (rows + 31) / 32 * 32;   // whole warps stay in the loop (warp-wide votes below)
+    for (uint64_t i = tid; i < rows_pad; i += stride) {
+        uint32_t vote = 0;
+        if (i < rows) {
+            const uint32_t a = row_ptr[i], b = row_ptr[i + 1];
+            if (b < a || b > nnz) {
+                bad = true;
+            } else {
+                const uint32_t len = b - a;
+                m = max(m, len);
+                if (len >= 3 && len <= 64) {
+                    const uint32_t s = line_length_of_row(col_idx + a, len, i + row_offset);
+                    vote = (s >= kStrideMin && s <= kStrideMax) ? s : 0xFFFFFFFFu;   // all-ones: voted "no line"
+                }
+            }
+        }
+        // warp-aggregated histogram update: one atomic per distinct vote in the warp
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, vote);
+        if (vote && lane == (uint32_t)(__ffs(peers) - 1)) {
+            atomicAdd(stats + kStatVoters, (uint32_t)__popc(peers));
+            if (vote != 0xFFFFFFFFu) atomicAdd(stats + kStatHist + vote, (uint32_t)__popc(peers));
+        }
+    }
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if (lane == 0 && m) atomicMax(stats + kStatMaxLen, m);
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicExch(stats + kStatBadRowPtr, 1u);
 }
 
-int launch_col_range(const uint32_t *col_idx, uint64_t nnz, uint32_t *min_max, cudaStream_t stream)
+int launch_csr_stats(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, uint64_t nnz, uint64_t row_offset, uint32_t *stats,
+                     cudaStream_t stream)
 {
-    if (nnz == 0) return BSM_OK;
-    col_range_kernel<<<grid_for(nnz, 256), 256, 0, stream>>>(col_idx, nnz, min_max);
+    csr_stats_kernel<<<grid_for(std::max(rows, nnz), 256), 256, 0, stream>>>(row_ptr, col_idx, rows, nnz, row_offset, stats);
     BSM_CUDA(cudaGetLastError());
     count_launch();
     return BSM_OK;
@@ -235,7 +252,8 @@ static int launch_transpose(int dtype, const void *src, void *dst, uint64_t rows
 {
     if (rows == 0 || cols == 0) return BSM_OK;
     const uint64_t ntiles = ((cols + 31) / 32) * ((rows + 31) / 32);
-    const int grid = (int)(ntiles < 148ull * 32 ? ntiles : 148ull * 32);
+    const uint64_t max_grid = (uint64_t)(rt().sm_count > 0 ? rt().sm_count : 148) * 32;
+    const int grid = (int)(ntiles < max_grid ? ntiles : max_grid);
     dim3 block(32, 8);
     if (dtype == BSM_F64)
         transpose_kernel<double, TO_ROWMAJOR><<<grid, block, 0, stream>>>((const double *)src, (double *)dst, rows, cols, ld);
@@ -353,7 +371,7 @@ __global__ void count_nonzero_kernel(const T *__restrict__ d, uint64_t rows, uin
             local += n;
         }
     }
-    if (lane == 0 && local) atomicAdd(total, local);
+    if (total && lane == 0 && local) atomicAdd(total, local);
 }
 
 template <typename T>
@@ -404,6 +422,101 @@ int launch_scatter_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t
         scatter_nonzero_kernel<double><<<grid, 256, 0, stream>>>((const double *)dense, rows, cols, ld, row_ptr, (double *)vals, col_idx);
     else
         scatter_nonzero_kernel<float><<<grid, 256, 0, stream>>>((const float *)dense, rows, cols, ld, row_ptr, (float *)vals, col_idx);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+// ---- pieces of the pipelined host call (pipeline.cu) ------------------------------------------------------------
+// smallest / largest stored column of every block of `block_rows` consecutive rows: which window of B a row block reads
+__global__ void block_col_range_kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col_idx, uint64_t rows,
+                                       uint64_t block_rows, uint32_t *__restrict__ out)
+{
+    const uint64_t k = blockIdx.y;
+    const uint64_t r0 = k * block_rows, r1 = min(rows, r0 + block_rows);
+    const uint32_t e0 = row_ptr[r0], e1 = row_ptr[r1];
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint64_t i = (uint64_t)e0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e1; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = col_idx[i];
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(out + 2 * k, lo);
+        atomicMax(out + 2 * k + 1, hi);
+    }
+}
+
+int launch_block_col_range(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, uint64_t block_rows, uint32_t nblocks,
+                           uint32_t *out, cudaStream_t stream)
+{
+    if (nblocks == 0) return BSM_OK;
+    if (nblocks > 65535) return fail(BSM_ERR_INVALID_ARGUMENT, "block_col_range: too many row blocks");
+    const int gx = std::max(1, grid_for(rows, 256) / (int)nblocks);
+    block_col_range_kernel<<<dim3(gx, nblocks), 256, 0, stream>>>(row_ptr, col_idx, rows, block_rows, out);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+// scatter of the zero-dropped entries of a row block straight into the reference's result layout: values and
+// usize (u64) column indices, positions from the block-local exclusive scan
+template <typename T>
+__global__ void scatter_nonzero64_kernel(const T *__restrict__ d, uint64_t rows, uint64_t cols, uint64_t ld,
+                                         const uint32_t *__restrict__ row_ptr, T *__restrict__ vals, uint64_t *__restrict__ col_index)
+{
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+        uint32_t pos = row_ptr[r];
+        for (uint64_t c0 = 0; c0 < cols; c0 += 32) {
+            const uint64_t c = c0 + lane;
+            T x = T(0);
+            if (c < cols) x = d[r * ld + c];
+            const bool k = c < cols && keep(x);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, k);
+            if (k) {
+                const uint32_t o = pos + __popc(m & ((1u << lane) - 1u));   // ascending column = insertion order
+                vals[o] = x;
+                col_index[o] = c;
+            }
+            pos += __popc(m);
+        }
+    }
+}
+
+int launch_scatter_nonzero64(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, const uint32_t *row_ptr, void *vals,
+                             uint64_t *col_index, cudaStream_t stream)
+{
+    if (rows == 0) return BSM_OK;
+    const int grid = grid_for(rows * 32, 256);
+    if (dtype == BSM_F64)
+        scatter_nonzero64_kernel<double><<<grid, 256, 0, stream>>>((const double *)dense, rows, cols, ld, row_ptr, (double *)vals, col_index);
+    else
+        scatter_nonzero64_kernel<float><<<grid, 256, 0, stream>>>((const float *)dense, rows, cols, ld, row_ptr, (float *)vals, col_index);
+    BSM_CUDA(cudaGetLastError());
+    count_launch();
+    return BSM_OK;
+}
+
+// row_index piece of row block k in the reference layout: out64[i] = entries before the block (tot[k]) + the block-local
+// exclusive scan; tot[k+1] = tot[k] + entries of the block (local_rp[rows])
+__global__ void row_index_piece_kernel(const uint32_t *__restrict__ local_rp, uint64_t rows, unsigned long long *__restrict__ tot, uint32_t k,
+                                       uint64_t *__restrict__ out64)
+{
+    const unsigned long long base = tot[k];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += stride) out64[i] = base + local_rp[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) tot[k + 1] = base + local_rp[rows];
+}
+
+int launch_row_index_piece(const uint32_t *local_rp, uint64_t rows, unsigned long long *tot, uint32_t k, uint64_t *out64, cudaStream_t stream)
+{
+    row_index_piece_kernel<<<grid_for(std::max<uint64_t>(rows, 1), 256), 256, 0, stream>>>(local_rp, rows, tot, k, out64);
     BSM_CUDA(cudaGetLastError());
     count_launch();
     return BSM_OK;

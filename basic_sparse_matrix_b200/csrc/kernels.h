@@ -28,6 +28,10 @@ struct RowParams {
     uint32_t cap;        // staged entries per slice (multiple of 4)
     uint32_t stages;     // TMA ring depth per warp
     uint32_t flags;      // BSM_TUNE_*
+    uint32_t pf_rows;    // L2 prefetch distance in rows (0 = off): the owner of row r prefetches B row (r + pf_rows) of its diagonal
+    uint32_t pf_bytes;   // bytes of one B row of this pass (multiple of 16)
+    uint32_t pf_limit;   // local rows r for which B row r exists
+    const char *pf_base; // B row of local row 0, first column of this pass (16-byte aligned)
     uint32_t n_peers;    // scatter variant: further destinations of every C row (0 = none)
     char *peers[7];      // their C pointers, offset like C (first column of the pass, this rank's first row)
 };
@@ -58,8 +62,8 @@ struct MergeParams {
 size_t merge_kernel_smem_bytes(int dtype, Shape sh, int block, uint32_t items);
 int launch_merge_partition(const uint32_t *row_ptr, uint32_t rows, uint32_t nnz, uint32_t items,
                            uint32_t num_chunks, uint32_t *part_rows, cudaStream_t stream);
-int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, cudaStream_t stream,
-                      int *grid_out);
+int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, int ctas_per_sm /* 0 = as many as fit */,
+                      cudaStream_t stream, int *grid_out);
 int launch_merge_fixup(int dtype, const MergeParams &p, cudaStream_t stream, int *launched);
 
 // ---- row-block kernel for band-like matrices (spmm_rowblock.cu) --------------------------------------
@@ -77,13 +81,14 @@ struct RowBlockParams {
 // out[1] += blocks holding a row whose stored columns are not a run of consecutive indices
 int launch_rowblock_probe(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, unsigned long long *out, cudaStream_t stream);
 int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p, int rows_per_block /* 4 or 8 */, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
-                         int *grid_out, int *block_out, int *smem_out);
+                         int *grid_out, int *block_out, int *smem_out, int *rb_out);
 
 // ---- format conversion / construction (convert.cu) ---------------------------------------------
 int launch_narrow_u64(const uint64_t *src, uint32_t *dst, uint64_t count, uint64_t bound, uint64_t subtract,
                       uint32_t *flag /* set to 1 when (v - subtract) >= bound */, cudaStream_t stream);
-int launch_row_stats(const uint32_t *row_ptr, uint64_t rows, uint32_t *max_len, uint32_t *bad_flag, cudaStream_t stream);
-int launch_col_range(const uint32_t *col_idx, uint64_t nnz, uint32_t *min_max /* [2], preset to {~0u, 0} */, cudaStream_t stream);
+// per-matrix statistics in one kernel; `stats` = kStatWords u32 (line_length.h), zeroed except [kStatColMin] = ~0u
+int launch_csr_stats(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, uint64_t nnz, uint64_t row_offset, uint32_t *stats,
+                     cudaStream_t stream);
 int launch_residual_norms(int dtype, const void *x, uint64_t ldx, const void *y, uint64_t ldy, uint64_t rows, uint64_t cols,
                           double *partial, cudaStream_t stream);   // result in partial[scratch-2], partial[scratch-1]
 int residual_norm_scratch_doubles();
@@ -97,6 +102,12 @@ int launch_count_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t c
                          unsigned long long *total, cudaStream_t stream);
 int launch_scatter_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld,
                            const uint32_t *row_ptr, void *vals, uint32_t *col_idx, cudaStream_t stream);
+int launch_block_col_range(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, uint64_t block_rows, uint32_t nblocks,
+                           uint32_t *out /* [2*nblocks], preset to {~0u, 0} pairs */, cudaStream_t stream);
+int launch_scatter_nonzero64(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, const uint32_t *row_ptr, void *vals,
+                             uint64_t *col_index, cudaStream_t stream);
+int launch_row_index_piece(const uint32_t *local_rp, uint64_t rows, unsigned long long *tot /* [nblocks+1] */, uint32_t k, uint64_t *out64,
+                           cudaStream_t stream);
 int launch_fill_u32(uint32_t *dst, uint64_t count, uint32_t value, cudaStream_t stream);
 
 // ---- synthetic generators (gen.cu) -----------------------------------------------------------------

@@ -251,17 +251,10 @@ template <typename T, int V> static const void *merge_kernel_select_gnt(int G, i
         // staged A stream feeds 32/G entries (128-bit lanes, full-width shapes only)
         if constexpr (V * sizeof(T) == 16) {
             if (!fulln) return nullptr;
-            if (NT == 2) {
+            if (NT == 2) {   // the grouped shapes the sweeps kept (profiles/r1_sweep{x,y}_rmat_*.jsonl); 4 tiles never won
                 switch (G) {
                     case 16: return merge_kernel_ptr<T, V, 16, 2>(true);
                     case 8: return merge_kernel_ptr<T, V, 8, 2>(true);
-                    case 4: return merge_kernel_ptr<T, V, 4, 2>(true);
-                }
-            } else if (NT == 4) {
-                switch (G) {
-                    case 16: return merge_kernel_ptr<T, V, 16, 4>(true);
-                    case 8: return merge_kernel_ptr<T, V, 8, 4>(true);
-                    case 4: return merge_kernel_ptr<T, V, 4, 4>(true);
                 }
             }
         }
@@ -284,7 +277,6 @@ static const void *merge_kernel_select(int dtype, Shape sh, uint32_t n)
         if (sh.V == 2) return merge_kernel_select_gnt<double, 2>(sh.G, sh.NT, fulln);
     } else {
         if (sh.V == 1) return merge_kernel_select_gnt<float, 1>(sh.G, sh.NT, fulln);
-        if (sh.V == 2) return merge_kernel_select_gnt<float, 2>(sh.G, sh.NT, fulln);
         if (sh.V == 4) return merge_kernel_select_gnt<float, 4>(sh.G, sh.NT, fulln);
     }
     return nullptr;
@@ -307,7 +299,7 @@ int launch_merge_partition(const uint32_t *row_ptr, uint32_t rows, uint32_t nnz,
     return BSM_OK;
 }
 
-int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, cudaStream_t stream, int *grid_out)
+int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size_t smem, int ctas_per_sm, cudaStream_t stream, int *grid_out)
 {
     const void *k = merge_kernel_select(dtype, sh, p.n);
     if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_merge: no kernel for this lane shape");
@@ -315,6 +307,16 @@ int launch_spmm_merge(int dtype, Shape sh, const MergeParams &p, int block, size
     const uint32_t grid = (p.num_chunks + groups_per_cta - 1) / groups_per_cta;
     if (grid == 0) return BSM_OK;
     BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Shared-memory carve-out: exactly what the resident CTAs' stages need — the rest of the 228 KB stays L1, where the hot B
+    // rows of a power-law matrix live. ctas_per_sm > 0 caps the residency below what registers allow (fewer warps, larger L1).
+    BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int occ = 0;
+    BSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, block, smem));
+    if (occ < 1) return fail(BSM_ERR_CUDA, "spmm_merge: kernel does not fit on an SM");
+    const int resident = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ;
+    const size_t need = (size_t)resident * (smem + 1024 + 64);   // + the driver's per-CTA reservation and the static barrier
+    const int pct = (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     MergeParams pc = p;
     void *args[] = {&pc};
     BSM_CUDA(cudaLaunchKernel(k, dim3(grid), dim3(block), args, smem, stream));

@@ -43,7 +43,8 @@ __global__ void rowblock_probe_kernel(const uint32_t *__restrict__ row_ptr, cons
 // Shared memory: one stage of `cap` values per warp (the values of the warp's RPP * RB consecutive rows are one
 // contiguous piece of the value array: a single TMA bulk copy, cp.async.bulk -> UBLKCP, completing on the warp's
 // mbarrier) + the mbarriers. The value reads are then warp-broadcast LDS instead of scattered global loads.
-template <typename T, int V, int G, int RB, bool FULLN>
+// FUSED: the opt-in BSM_TUNE_FUSED arithmetic (one FMA per product; tolerance-level agreement with the reference)
+template <typename T, int V, int G, int RB, bool FULLN, bool FUSED>
 __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(const RowBlockParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
                 for (int r = 0; r < RB; ++r) {
                     const uint32_t off = j - first[r];
                     if (off < len[r]) {   // row r stores column j, at entry base + off; ascending j = stored order
-                        axpy_unfused<T, V>(va[base[r] + off], b.x, acc[r].x, negzero2);
+                        axpy<FUSED, T, V>(va[base[r] + off], b.x, acc[r].x, negzero2);
                     }
                 }
             }
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
                     if (col_ok) b.template load<false>(reinterpret_cast<const T *>(brow), 0ull);
 #pragma unroll
                     for (int r = 0; r < RB; ++r) {
-                        axpy_unfused<T, V>(vrow[r][j], b.x, acc[r].x, negzero2);
+                        axpy<FUSED, T, V>(vrow[r][j], b.x, acc[r].x, negzero2);
                     }
                 }
             }
@@ -170,44 +171,57 @@ int launch_rowblock_probe(const uint32_t *row_ptr, const uint32_t *col_idx, uint
     return BSM_OK;
 }
 
-template <typename T, int V, int G> static const void *rowblock_ptr(bool fulln, int rb)
+// Instantiations: 128-bit lanes (f64 x 2, f32 x 4) and one-element lanes (operands that are not 16-byte granular),
+// 4 / 8 / 16 / 32 lanes per row, blocks of 4 or 8 rows; the fused arithmetic for full-width 128-bit shapes only.
+// Anything else (2-element f32 lanes, 1 or 2 lanes per row) reports "no kernel": BSM_ALGO_AUTO then runs the plain vector kernel.
+// Blocks of 8 rows exist where they measured faster: a full warp per row with 128-bit lanes (r1_sweepag_band_*); else 4.
+template <typename T, int V, int G> constexpr bool rowblock_has_rb8() { return G == 32 && V * sizeof(T) == 16; }
+template <typename T, int V, int G> static const void *rowblock_ptr(bool fulln, int rb, bool fused)
 {
-    if (rb == 4)
-        return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, true>)
-                     : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, false>);
-    return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 8, true>)
-                 : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 8, false>);
+    if constexpr (rowblock_has_rb8<T, V, G>()) {
+        if (rb == 8) {
+            if (fused) return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 8, true, true>) : nullptr;
+            return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 8, true, false>)
+                         : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 8, false, false>);
+        }
+    }
+    if constexpr (V * sizeof(T) == 16) {
+        if (fused && fulln) return reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, true, true>);
+    }
+    if (fused) return nullptr;
+    return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, true, false>)
+                 : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, false, false>);
 }
-template <typename T, int V> static const void *rowblock_select_g(int G, bool fulln, int rb)
+template <typename T, int V> static const void *rowblock_select_g(int G, bool fulln, int rb, bool fused)
 {
     switch (G) {
-        case 32: return rowblock_ptr<T, V, 32>(fulln, rb);
-        case 16: return rowblock_ptr<T, V, 16>(fulln, rb);
-        case 8: return rowblock_ptr<T, V, 8>(fulln, rb);
-        case 4: return rowblock_ptr<T, V, 4>(fulln, rb);
-        case 2: return rowblock_ptr<T, V, 2>(fulln, rb);
-        case 1: return rowblock_ptr<T, V, 1>(fulln, rb);
+        case 32: return rowblock_ptr<T, V, 32>(fulln, rb, fused);
+        case 16: return rowblock_ptr<T, V, 16>(fulln, rb, fused);
+        case 8: return rowblock_ptr<T, V, 8>(fulln, rb, fused);
+        case 4: return rowblock_ptr<T, V, 4>(fulln, rb, fused);
     }
     return nullptr;
 }
 
 int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p_in, int rb, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
-                         int *grid_out, int *block_out, int *smem_out)
+                         int *grid_out, int *block_out, int *smem_out, int *rb_out)
 {
     if (sh.NT != 1) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rowblock: one register tile per lane only");
     const bool fulln = p_in.n == (uint32_t)(sh.V * sh.G);
     const void *k = nullptr;
-    if (dtype == BSM_F64) {
-        if (sh.V == 1) k = rowblock_select_g<double, 1>(sh.G, fulln, rb);
-        if (sh.V == 2) k = rowblock_select_g<double, 2>(sh.G, fulln, rb);
-    } else {
-        if (sh.V == 1) k = rowblock_select_g<float, 1>(sh.G, fulln, rb);
-        if (sh.V == 2) k = rowblock_select_g<float, 2>(sh.G, fulln, rb);
-        if (sh.V == 4) k = rowblock_select_g<float, 4>(sh.G, fulln, rb);
-    }
-    if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rowblock: no kernel for this lane shape");
-    RowBlockParams pc = p_in;
+    const bool fused = (p_in.flags & BSM_TUNE_FUSED) != 0;
     if (rb != 4 && rb != 8) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_rowblock: 4 or 8 rows per block");
+    if (rb == 8 && !(sh.G == 32 && sh.V * dtype_size(dtype) == 16)) rb = 4;   // blocks of 8 rows: full-warp 128-bit shapes only
+    if (rb_out) *rb_out = rb;
+    if (dtype == BSM_F64) {
+        if (sh.V == 1) k = rowblock_select_g<double, 1>(sh.G, fulln, rb, fused);
+        if (sh.V == 2) k = rowblock_select_g<double, 2>(sh.G, fulln, rb, fused);
+    } else {
+        if (sh.V == 1) k = rowblock_select_g<float, 1>(sh.G, fulln, rb, fused);
+        if (sh.V == 4) k = rowblock_select_g<float, 4>(sh.G, fulln, rb, fused);
+    }
+    if (!k) return fail(BSM_ERR_NOT_SUPPORTED, fused ? "spmm_rowblock: BSM_TUNE_FUSED exists for full-width 128-bit lane shapes only" : "spmm_rowblock: no kernel for this lane shape");
+    RowBlockParams pc = p_in;
     const uint64_t wr = (uint64_t)(32 / sh.G) * (uint64_t)rb;                  // rows per warp block
     const uint64_t cap = ((wr * max_row_nnz + 3 + 3) & ~3ull) + 4;             // + aligned start, rounded size
     int block = 256;

@@ -5,7 +5,6 @@ namespace bsm {
 const void *row_kernel_select_f32(Shape sh, bool fulln, int flavour, bool multi)
 {
     if (sh.V == 1) return row_kernel_select_v<float, 1>(sh, fulln, flavour, multi);
-    if (sh.V == 2) return row_kernel_select_v<float, 2>(sh, fulln, flavour, multi);
     if (sh.V == 4) return row_kernel_select_v<float, 4>(sh, fulln, flavour, multi);
     return nullptr;
 }

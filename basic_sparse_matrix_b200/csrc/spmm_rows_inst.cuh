@@ -13,33 +13,39 @@ static const void *rk()
     return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI>);
 }
 
-// Register-budget flavours (`flavour` argument of the selectors):
-//   0: CTAs of up to 512 threads, 1 per SM (<= 128 registers)       — the default
-//   1: same, gather window twice as deep
-//   2: CTAs of up to 256 threads, 3 per SM (<= 85 registers)
-//   3: (retired: 4 CTAs of 256 threads at <= 64 registers spilled and measured slower; runs as 2)
-//   4: flavour 2 with scalar (one LDS per entry) instead of LDS.128 reads of col_idx / values
-//   5, 6: one CTA of up to 768 threads per SM (<= 85 registers), LDS.128 / scalar reads
-//   7: flavour 6 with a window of 10 gathers when a lane holds one register tile (else flavour 4)
+// Register-budget flavours (`flavour` argument of the selectors = bsm_tuning.reg_flavour - 1):
+//   0: CTAs of up to 512 threads, 1 per SM (<= 128 registers), LDS.128 reads of the staged col_idx / values
+//   4: CTAs of up to 256 threads, 3 per SM (<= 85 registers), scalar reads (one LDS per entry)  — default for several tiles per lane
+//   6: one CTA of up to 768 threads per SM (<= 85 registers), scalar reads                       — default for grouped lanes
+//   7: flavour 6 with a window of 10 gathers when a lane holds one register tile (else flavour 4) — default for one tile per lane
+//   (narrow one-tile shapes: 0, and for a row per lane 4 = scalar reads)
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
+// Flavours 1, 2, 3, 5 of round 1 (window twice as deep; LDS.128 reads at 3 CTAs / at 768 threads; 4 CTAs at 64 registers) lost
+// every sweep they were in (profiles/r1_sweep{i,s}_*.jsonl) and are no longer built: 1 runs as 0, 2 and 3 as 4, 5 as 6.
 // G == 32 shapes with all columns valid exist in all; everything else in flavours 0 and -1 only.
 // `multi` (scatter of C rows to peer GPUs) exists for the default flavour of every shape and for the unstaged one.
+inline int row_flavour_built(int flavour)
+{
+    switch (flavour) {
+        case 1: return 0;
+        case 2:
+        case 3: return 4;
+        case 5: return 6;
+    }
+    return flavour;
+}
+
 template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int flavour, bool multi)
 {
-    constexpr int U1 = row_default_u(NT), U2 = 2 * U1;
-    if (multi) {
-        if (flavour < 0) return fulln ? rk<T, V, 32, NT, true, U1, 512, 1, false, true, true>() : rk<T, V, 32, NT, false, U1, 512, 1, false, true, true>();
-        if (!fulln) return rk<T, V, 32, NT, false, U1, 512, 1, true, true, true>();
-        return flavour == 4 ? rk<T, V, 32, NT, true, U1, 256, 3, true, false, true>() : rk<T, V, 32, NT, true, U1, 256, 3, true, true, true>();
-    }
-    if (flavour < 0) return fulln ? rk<T, V, 32, NT, true, U1, 512, 1, false>() : rk<T, V, 32, NT, false, U1, 512, 1, false>();
+    constexpr int U1 = row_default_u(NT);
+    flavour = row_flavour_built(flavour);
+    // scatter variant: bound by the P2P stores over NVLink, not by the SM — one (predicated, staged) kernel per shape
+    if (multi) return flavour < 0 ? nullptr : rk<T, V, 32, NT, false, U1, 512, 1, true, true, true>();
+    if (flavour < 0) return rk<T, V, 32, NT, false, U1, 512, 1, false>();   // unstaged: one (predicated) variant serves full-width shapes too
     if (fulln) {
         switch (flavour) {
-            case 1: return rk<T, V, 32, NT, true, U2, 512, 1>();
-            case 2: return rk<T, V, 32, NT, true, U1, 256, 3>();
-            case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // flavour 2 with scalar A-stream reads
-            case 5: return rk<T, V, 32, NT, true, U1, 768, 1>();               // ONE CTA of 24 warps per SM (24 adjacent lines share L1)
-            case 6: return rk<T, V, 32, NT, true, U1, 768, 1, true, false>();  //   " with scalar A-stream reads
+            case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();
+            case 6: return rk<T, V, 32, NT, true, U1, 768, 1, true, false>();  // ONE CTA of 24 warps per SM (24 adjacent lines share L1)
             case 7:   // one tile per lane: window of 10 gathers — as deep as 85 registers allow without spilling
                 if constexpr (NT == 1) return rk<T, V, 32, NT, true, 10, 768, 1, true, false>();
                 else return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // (deeper windows measured slower with several tiles)
@@ -51,12 +57,11 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
 
 template <typename T, int V, int G> static const void *rk_narrow(bool fulln, int flavour, bool multi)
 {
-    if (multi) {
-        if (flavour < 0) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, false, true, true>() : rk<T, V, G, 1, false, 8, 512, 1, false, true, true>();
-        return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, true, true>() : rk<T, V, G, 1, false, 8, 512, 1, true, true, true>();
+    if (multi) return flavour < 0 ? nullptr : rk<T, V, G, 1, false, 8, 512, 1, true, true, true>();   // scatter variant (see rk_wide)
+    if (flavour < 0) return rk<T, V, G, 1, false, 8, 512, 1, false>();   // unstaged: one (predicated) variant
+    if constexpr (G == 1) {   // a row per lane (SpMV): scalar reads of the staged col_idx / values
+        if (flavour == 4) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, false>() : rk<T, V, G, 1, false, 8, 512, 1, true, false>();
     }
-    if (flavour < 0) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, false>() : rk<T, V, G, 1, false, 8, 512, 1, false>();
-    if (flavour == 4) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, false>() : rk<T, V, G, 1, false, 8, 512, 1, true, false>();   // scalar A reads
     return fulln ? rk<T, V, G, 1, true, 8, 512, 1>() : rk<T, V, G, 1, false, 8, 512, 1>();
 }
 
@@ -66,6 +71,7 @@ template <typename T, int V, int G, int NT> static const void *rk_grouped(bool f
 {
     constexpr int U1 = row_default_u(NT);
     if (!fulln || multi) return nullptr;
+    flavour = row_flavour_built(flavour);
     if (flavour == 6) return rk<T, V, G, NT, true, U1, 768, 1, true, false>();
     return rk<T, V, G, NT, true, U1, 256, 3, true, false>();
 }

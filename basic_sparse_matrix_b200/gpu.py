@@ -56,6 +56,21 @@ def last_launch_info() -> dict:
     return info.as_dict()
 
 
+def phase_timers(enable: bool | None = None, reset: bool = True) -> dict:
+    """Where the time of the host-to-host calls went since the last reset (seconds per phase); ``enable`` switches
+    the timers on or off first."""
+    if enable is not None:
+        check(lib().bsm_phase_timers_enable(1 if enable else 0))
+    buf = (C.c_double * 16)()
+    check(lib().bsm_phase_timers_read(buf, 16, 1 if reset else 0))
+    out = {}
+    for i in range(16):
+        name = lib().bsm_phase_name(i).decode()
+        if name:
+            out[name] = buf[i]
+    return out
+
+
 def device_info() -> dict:
     sm, cc1, cc2 = C.c_int(0), C.c_int(0), C.c_int(0)
     l2, hbm = C.c_size_t(0), C.c_size_t(0)

@@ -200,11 +200,35 @@ class Csr(GetDims):
             L.bsm_host_free(orow)
         return Csr.from_raw_parts((self.dims.rows, rhs.col_count), rv, rc, rr)
 
+    def mul_dense_csr_into(self, rhs: Dense, out_v: np.ndarray, out_col_index: np.ndarray, out_row_index: np.ndarray,
+                           algo: str = "auto") -> "Csr":
+        """The literal ``mul_dense`` into caller-provided result arrays (``bsm_mul_dense_host_into_*``): ``out_v`` /
+        ``out_col_index`` hold up to ``len(out_v)`` entries, ``out_row_index`` rows+1.  Returns a ``Csr`` VIEW of the arrays
+        (no copy).  With pinned arrays the device->host copies overlap the computation; this is the end-to-end call
+        ``bench.py`` times."""
+        if self.dims.cols != rhs.get_dims().rows:
+            raise MatError(MatErr.IncorrectDimensions)
+        self._check_multipliable()
+        if rhs.dtype != self.dtype or out_v.dtype != self.dtype:
+            raise TypeError("Csr, Dense and the result values must have the same element type")
+        if out_col_index.dtype != np.uint64 or out_row_index.dtype != np.uint64 or len(out_row_index) < self.dims.rows + 1:
+            raise TypeError("result indices are usize (uint64); row_index needs rows+1 entries")
+        sfx = _lib.suffix(self.dtype)
+        v, ci, ri = self.raw_parts()
+        cols = [np.ascontiguousarray(c) for c in rhs.data]
+        out_nnz = C.c_uint64(0)
+        _lib.check(getattr(_lib.lib(), f"bsm_mul_dense_host_into_{sfx}")(
+            self.dims.rows, self.dims.cols, len(v), _lib.ptr(v), _lib.ptr(ci), _lib.ptr(ri), len(ri),
+            rhs.row_count, rhs.col_count, _lib.col_ptr_array(cols), _lib.ALGO_NAMES[algo],
+            min(len(out_v), len(out_col_index)), _lib.ptr(out_v), _lib.ptr(out_col_index), _lib.ptr(out_row_index), C.byref(out_nnz)))
+        nnz = out_nnz.value
+        return Csr.from_raw_parts((self.dims.rows, rhs.col_count), out_v[:nnz], out_col_index[:nnz], out_row_index[:self.dims.rows + 1])
+
     def mul_dense_into(self, rhs: Dense, out: Dense | None = None, algo: str = "auto") -> Dense:
         """Same product as ``mul_dense`` with a DENSE result in the reference's column-major layout
         (no zero-drop): host ``Csr`` and host ``Dense`` in, host ``Dense`` out, through the pipelined
-        C-ABI call ``bsm_mul_dense_host_dense_*`` (H2D, multiply and D2H overlap per column group).
-        This is the end-to-end call ``bench.py`` times; pass pinned column buffers for full overlap."""
+        C-ABI call ``bsm_mul_dense_host_dense_*`` (chunks of B rows in, blocks of output rows out, overlapped).
+        ``bench.py`` reports it as ``e2e_dense``; pass pinned column buffers for full overlap."""
         if self.dims.cols != rhs.get_dims().rows:
             raise MatError(MatErr.IncorrectDimensions)
         self._check_multipliable()

@@ -72,6 +72,11 @@ typedef enum bsm_algo {
 /* bsm_tuning.flags */
 #define BSM_TUNE_A_EVICT_FIRST 0x1u   /* L2 evict-first policy on the TMA bulk copies of col_idx/values */
 #define BSM_TUNE_C_STREAMING   0x2u   /* st.global.cs for C rows                                       */
+#define BSM_TUNE_FUSED         0x4u   /* OPT-IN: one fused multiply-add per product instead of the reference's separately
+                                         rounded multiply and add (sparse.rs:438-439). Halves the FP instructions of the
+                                         row-block kernel; results then agree with the reference within north_star's
+                                         tolerance (1e-12 f64 / 1e-5 f32 of sum|a*b|) instead of bit for bit. Never a
+                                         default. The merge-path kernel is always fused.                               */
 #define BSM_TUNE_DEFAULT_FLAGS (BSM_TUNE_A_EVICT_FIRST | BSM_TUNE_C_STREAMING)
 
 /* Launch tuning; all-zero = library heuristics. Used by the bench sweeps and tests. */
@@ -90,17 +95,19 @@ typedef struct bsm_tuning {
     int32_t prefer_wide_rows;/* vector kernel: 1 = a full warp per row even when 128-bit loads need fewer
                                 lanes; merge-path does that by default, -1 turns it off there       */
     int32_t reg_flavour;     /* vector kernel: register-budget variant. 0 = heuristic; 1 = CTAs of <= 512
-                                threads, 1 per SM; 2 = same with a gather window twice as deep;
-                                3 = CTAs of <= 256 threads, 3 per SM; 4 = retired (runs as 3);
-                                5 = 3 with scalar instead of LDS.128 reads of col_idx / values;
-                                6 / 7 = one CTA of <= 768 threads per SM, LDS.128 / scalar reads;
-                                8 = 7 with a window of 10 gathers (one register tile per lane)
+                                threads, 1 per SM; 5 = CTAs of <= 256 threads, 3 per SM, scalar reads of the staged
+                                col_idx / values; 7 = one CTA of <= 768 threads per SM, scalar reads; 8 = 7 with a
+                                window of 10 gathers (one register tile per lane). 2, 3, 4, 6 = variants the round-1
+                                sweeps rejected (deeper window, LDS.128 reads): no longer built, they run as 1, 5, 5, 7
                                 (see csrc/spmm_rows_inst.cuh)                                        */
     int32_t lanes_per_row;   /* vector kernel: lanes that share one output row (power of two <= 32). 0 = heuristic.
                                 Fewer lanes than the 128-bit loads need -> 2 or 4 register tiles per lane and
                                 32/lanes rows side by side, each lane group walking its own flat entry stream:
                                 one LDS of the A stream then feeds 32/lanes rows                            */
-    int32_t reserved[4];
+    int32_t b_prefetch;      /* vector kernel on stencil-like matrices: the owner of row r asks the TMA unit to prefetch
+                                B row r + b_prefetch (the row its diagonal entry will read) into L2. 0 = heuristic,
+                                -1 = off                                                                            */
+    int32_t reserved[3];
 } bsm_tuning;
 
 /* what the last bsm_spmm* call on this thread actually launched */
@@ -115,8 +122,9 @@ typedef struct bsm_launch_info {
     int32_t rows_per_slice, stages, capacity;   /* capacity 0 = col_idx/values not staged */
     int32_t passes;          /* column-tile passes                                                  */
     int32_t merge_items, merge_chunks;
-    int32_t rows_per_warp, reg_flavour, col_tile;
-    int32_t reserved[1];
+    int32_t rows_per_warp, reg_flavour;
+    int32_t col_tile;        /* columns of the FIRST pass (same meaning in bsm_spmm* and bsm_plan_vector)          */
+    int32_t b_prefetch;      /* rows of L2 prefetch distance the launch used (0 = none)                             */
 } bsm_launch_info;
 
 /* ------------------------------------------------------------------------------------------
@@ -231,10 +239,26 @@ int bsm_mul_dense_host_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const flo
                            uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
                            const float *const *rhs_col_ptrs, int algo, uint64_t *out_nnz,
                            float **out_v, uint64_t **out_col_index, uint64_t **out_row_index);
+/* The same literal call into CALLER-PROVIDED result arrays (out_v / out_col_index: room for `capacity` entries;
+ * out_row_index: rows + 1): what a binding uses to fill a Csr whose Vecs it allocated (Vec::with_capacity), and what
+ * bench.py times end to end with pinned arrays. rows * rhs_cols entries always suffice; too small a capacity fails
+ * with BSM_ERR_INVALID_ARGUMENT (nothing useful is left in the arrays). The call is pipelined: B travels host -> device
+ * in chunks of rows, each block of output rows is multiplied as soon as the B rows its columns reach have landed, and
+ * its zero-dropped entries (values + usize columns + its row_index piece) travel device -> host while the next block
+ * is computed. Use pinned host memory for the copies to overlap. */
+int bsm_mul_dense_host_into_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v,
+                                const uint64_t *col_index, const uint64_t *row_index,
+                                uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                                const double *const *rhs_col_ptrs, int algo, uint64_t capacity, double *out_v,
+                                uint64_t *out_col_index, uint64_t *out_row_index, uint64_t *out_nnz);
+int bsm_mul_dense_host_into_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const float *v,
+                                const uint64_t *col_index, const uint64_t *row_index,
+                                uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
+                                const float *const *rhs_col_ptrs, int algo, uint64_t capacity, float *out_v,
+                                uint64_t *out_col_index, uint64_t *out_row_index, uint64_t *out_nnz);
 /* Same product with a DENSE result in the reference's column-major layout: host Csr and host Dense
- * columns in, host Dense columns out (out_col_ptrs[c] has room for `rows` elements). Pipelined over
- * groups of columns so that host->device copies, the multiplication and device->host copies
- * overlap; use pinned host buffers for the overlap to materialise. */
+ * columns in, host Dense columns out (out_col_ptrs[c] has room for `rows` elements). The same pipeline
+ * (chunks of B rows in, blocks of output rows out); use pinned host buffers for the overlap to materialise. */
 int bsm_mul_dense_host_dense_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v,
                                  const uint64_t *col_index, const uint64_t *row_index,
                                  uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
@@ -307,6 +331,14 @@ int bsm_gen_band(int dtype, uint64_t n, uint64_t hb, uint64_t row_begin, uint64_
  * kept; values from the hash in the given mode. */
 int bsm_gen_rmat(int dtype, int scale, uint64_t edges, double a, double b, double c, uint64_t seed,
                  int mode, bsm_csr **out);
+
+/* Where the time of the host-to-host calls goes (diagnostics; off unless BSM_PHASE_TIMERS=1 or enabled here).
+ * bsm_phase_timers_read copies the accumulated seconds of the first `count` phases (bsm_phase_name(i), "" past the
+ * last) and optionally resets them: wall time of the A upload and of the whole call and of the host's waits, device
+ * busy time of the H2D copies, transposes, SpMM, result construction and D2H copies. */
+int bsm_phase_timers_enable(int on);
+int bsm_phase_timers_read(double *seconds, int count, int reset);
+const char *bsm_phase_name(int phase);
 
 /* raw device memory helpers for callers that keep their own buffers */
 int bsm_l2_flush(void);   /* overwrite a buffer larger than L2 (timing hygiene) */

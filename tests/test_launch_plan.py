@@ -165,10 +165,11 @@ def test_every_plan_is_launchable(dtype, rows, mean, spread, stride, n, tune):
 
 
 @pytest.mark.parametrize("dtype,n,first,passes", [(F32, 129, 128, 2), (F64, 129, 128, 2), (F64, 255, 254, 2), (F32, 258, 256, 2),
-                                                   (F32, 513, 512, 2), (F64, 300, 256, 2), (F32, 300, 300, 1), (F32, 130, 130, 1)])
+                                                   (F32, 513, 512, 2), (F64, 300, 256, 2), (F32, 300, 300, 1), (F32, 130, 128, 2), (F64, 130, 130, 1)])
 def test_pass_width_when_alignment_forces_narrow_vectors(dtype, n, first, passes):
     """129 f32 columns are 129 one-element lanes — more than four register tiles of 32 lanes hold. The pass is cut to a
-    width the 16-byte vectors divide (128) and the rest goes to the next pass; before this the last column was dropped."""
+    width the 16-byte vectors divide (128) and the rest goes to the next pass; before this the last column was dropped.
+    (f32 lanes are 4 elements or 1: 130 f32 columns are one-element lanes too — there are no 2-element f32 kernels.)"""
     p = plan(dtype, 1_000_000, 7_000_000, 7, 0, n)
     assert (p["col_tile"], p["passes"]) == (first, passes)
     assert p["lanes_per_row"] * p["reg_tiles"] * p["vec_elems"] >= first
