@@ -10,11 +10,11 @@ from .dense import Dense
 from .sparse import Csr, CsrEntry
 from .util import GetDims, MatDim, MatErr, MatError
 
-__all__ = ["Csr", "CsrEntry", "Dense", "GetDims", "MatDim", "MatErr", "MatError", "gpu", "gen"]
+__all__ = ["Csr", "CsrEntry", "Dense", "GetDims", "MatDim", "MatErr", "MatError", "gpu", "gen", "solve"]
 
 
 def __getattr__(name):
-    if name in ("gpu", "gen"):
+    if name in ("gpu", "gen", "solve"):
         import importlib
         return importlib.import_module(f".{name}", __name__)
     raise AttributeError(name)

@@ -140,6 +140,8 @@ def _declare(L):
     sig("bsm_kernel_launch_count", u64)
     sig("bsm_dense_to_csr", i32, vp, PV)
     sig("bsm_dense_residual_norm", i32, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double))
+    sig("bsm_forward_substitution", i32, vp, vp, vp)
+    sig("bsm_backward_substitution", i32, vp, vp, vp)
     sig("bsm_host_free", None, vp)
     sig("bsm_partition_rows", i32, vp, u64, i32, vp)
     sig("bsm_comm_unique_id", i32, C.c_char_p)

@@ -179,7 +179,7 @@ static int spmm_merge(const bsm_csr *a_const, const bsm_dense *b, bsm_dense *c, 
         if (want_g > 0) {
             const Shape sv = pick_shape(n, b->ld, c->ld, col0, b->data, c->data, s, false, ldcar);
             const int g = want_g, nt = sv.V * (int)s == 16 ? (int)(n / (uint32_t)(sv.V * g)) : 0;
-            if ((g == 16 || g == 8 || g == 4) && (nt == 2 || nt == 4) && n == (uint32_t)(sv.V * g * nt)) {
+            if ((g == 16 || g == 8) && nt == 2 && n == (uint32_t)(sv.V * g * nt)) {   // the grouped merge shapes that are built
                 sh.V = sv.V;
                 sh.G = g;
                 sh.NT = nt;

@@ -118,6 +118,15 @@ template <typename T> struct HostProduct {
 
 constexpr uint64_t kBlockBytes = 256ull << 20;   // C rows per block: about this many bytes of row-major result
 constexpr uint64_t kChunkBytes = 128ull << 20;   // B rows per chunk
+// BSM_PIPE_BLOCK_BYTES / BSM_PIPE_CHUNK_BYTES override the two (the tests shrink them to drive many blocks and chunks
+// through small matrices)
+static uint64_t env_bytes(const char *name, uint64_t dflt)
+{
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    const unsigned long long v = strtoull(e, nullptr, 10);
+    return v ? (uint64_t)v : dflt;
+}
 
 template <typename T> int host_product(const HostProduct<T> &q)
 {
@@ -151,13 +160,13 @@ template <typename T> int host_product(const HostProduct<T> &q)
     DevTimeline tl;
     // geometry
     const uint64_t ld = default_ld(n, q.dtype);
-    uint64_t rb = std::max<uint64_t>(4, kBlockBytes / (ld * s) / 4 * 4);       // rows per block (multiple of 4: the row_ptr
+    uint64_t rb = std::max<uint64_t>(4, env_bytes("BSM_PIPE_BLOCK_BYTES", kBlockBytes) / (ld * s) / 4 * 4);       // rows per block (multiple of 4: the row_ptr
     if (a->row_stride && rb > a->row_stride) rb = rb / a->row_stride * a->row_stride;   // window of a view stays 16-byte
     if (rb % 4) rb = (rb + 3) / 4 * 4;                                           // aligned); whole stencil lines
     rb = std::min(rb, (rows + 3) / 4 * 4);
     if ((rows + rb - 1) / rb > 4096) rb = ((rows + 4095) / 4096 + 3) / 4 * 4;
     const uint32_t nblocks = (uint32_t)((rows + rb - 1) / rb);
-    const uint64_t cb = std::max<uint64_t>(32, kChunkBytes / (n * s) / 32 * 32);   // B rows per chunk
+    const uint64_t cb = std::max<uint64_t>(32, env_bytes("BSM_PIPE_CHUNK_BYTES", kChunkBytes) / (n * s) / 32 * 32);   // B rows per chunk
     // window of B rows A references (a rank's row block of a banded / stencil matrix reads a window of B, not all of it)
     const bool has_entries = a->nnz != 0;
     const uint64_t win_lo = has_entries ? (uint64_t)a->col_min / 32 * 32 : 0;

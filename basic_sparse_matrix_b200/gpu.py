@@ -278,6 +278,24 @@ class DeviceCsr(_Handle):
         return out
 
 
+    def forward_substitution(self, b: DeviceDense, out: DeviceDense | None = None) -> DeviceDense:
+        """``forward_substitution(l, b)`` of the reference's ``solve`` (lib.rs:28-46) with ``self`` = L: solves L y = b for
+        every column of ``b`` on the device, bit-identical to the reference's sequential loops."""
+        if out is None:
+            bi = b.info()
+            out = DeviceDense.alloc(bi["rows"], bi["cols"], bi["dtype"])
+        check(lib().bsm_forward_substitution(self.handle, b.handle, out.handle))
+        return out
+
+    def backward_substitution(self, y: DeviceDense, out: DeviceDense | None = None) -> DeviceDense:
+        """``backward_substitution(l_star, y)`` (lib.rs:49-65) with ``self`` = L* (the transposed factor, diagonal first in
+        every row): solves L* x = y on the device."""
+        if out is None:
+            yi = y.info()
+            out = DeviceDense.alloc(yi["rows"], yi["cols"], yi["dtype"])
+        check(lib().bsm_backward_substitution(self.handle, y.handle, out.handle))
+        return out
+
     def mul_dense_scatter(self, rhs: DeviceDense, full_buffers, row_offset: int, algo="auto") -> None:
         """Fused multiply + all-gather: every finished C row goes to ``full_buffers[0]`` (this rank's full
         result) and to all the others (peer GPUs' full results, mapped with ``ipc_open``), at global row

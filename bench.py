@@ -10,10 +10,16 @@ Workload (BASELINE.json configs[3]): 3-D 7-point Laplacian on a 256^3 grid (16 7
 117 047 296 nnz) x dense 16 777 216 x 128, f64, row-partitioned over the N GPUs with nnz-balanced
 splits and B replicated (strong scaling: the problem is fixed, each rank owns a row block, no
 data-path collective).  A "step" is one pass of the hot path (one `Csr::mul_dense`) over the
-matrix.  `value` times the device-resident path with CUDA events; `e2e` times the same product
-through the reference-facing C-ABI calls from HOST buffers (upload A rows, upload B columns with
-the column-major -> row-major transpose, multiply, download C columns).  Operands are far larger
-than L2 (126 MB), so consecutive steps cannot hit in cache (no explicit flush needed).
+matrix.  `value` times the device-resident path with CUDA events.  `e2e` times the LITERAL reference
+call — host Csr x host Dense -> zero-dropped host Csr (sparse.rs:426-446 incl. the result construction) —
+through the C ABI from pinned host buffers (`bsm_mul_dense_host_into_*`: A up, B up in row chunks,
+SpMM + result construction per row block, values / usize columns / row_index down); `e2e_dense` is the
+same product returned as host Dense columns.  Operands are far larger than L2 (126 MB), so consecutive
+steps cannot hit in cache (no explicit flush needed).
+
+Every line carries `parity`: rows of this run's OWN device result (every rank's block; with the gathered
+result also rows owned by other ranks) recomputed by the CPU oracle and compared bit for bit, and
+`north_star_target`: the same matrix x 64 columns (>= 100 M nnz x 64, f64) in the same run.
 
 One JSON line is printed by rank 0.  `--impl reference` times the reference's own CPU
 implementation (the C restatement in oracle/, single-threaded like the Rust original) on the
@@ -196,6 +202,94 @@ def k_ref_of(kind, prm, rows_total, r0, r1):
     return min(rows_total, r1 + reach) - max(0, r0 - reach)
 
 
+ALGO_NAME = {1: "vector", 2: "merge", 3: "rowblock"}
+KERNEL_NAME = {1: "spmm_rows_kernel", 2: "spmm_merge_kernel", 3: "spmm_rowblock_kernel"}
+B_SEED = 5
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Pinned host buffers are first-touched by the allocating thread: run this process on the CPUs of the NUMA node the
+    GPU hangs off, so that every rank's H2D / D2H traffic stays on its own socket. Returns what was found."""
+    info = {"node": None, "cpus": None, "bound": False}
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus_txt = open(base + "/local_cpulist").read().strip()
+        info.update(node=node, cpus=cpus_txt, pci=bus)
+        cpus = set()
+        for part in cpus_txt.split(","):
+            if "-" in part:
+                lo, hi = part.split("-")
+                cpus.update(range(int(lo), int(hi) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            info["bound"] = True
+        info["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+    except Exception as ex:   # no sysfs / single node: nothing to bind
+        info["note"] = str(ex)[:120]
+    return info
+
+
+def parity_row_ids(r0, r1, count=64, reach=0, rows_total=None):
+    """Rows of the block [r0, r1) to recompute: its first and last rows, the rows one stencil reach inside it, and hashed rows."""
+    from basic_sparse_matrix_b200 import gen
+    nrows = r1 - r0
+    if nrows <= 0:
+        return np.zeros(0, np.int64)
+    ids = {r0, r0 + 1, r1 - 2, r1 - 1, r0 + nrows // 2}
+    if reach:
+        ids.update([r0 + reach - 1, r0 + reach, r1 - reach - 1, r1 - reach])
+    h = gen.hash_u64(977, np.arange(count, dtype=np.uint64) + np.uint64(r0))
+    ids.update(int(r0 + int(x) % nrows) for x in h)
+    return np.array(sorted(i for i in ids if r0 <= i < r1), dtype=np.int64)
+
+
+def oracle_rows(kind, prm, n, dtype, row_ids, a_host=None):
+    """The reference's value of the given GLOBAL rows of A x B (sequential sum in stored order, mul then add), recomputed
+    by the CPU oracle from the counter-based generators: no operand travels."""
+    from basic_sparse_matrix_b200 import gen
+    from oracle import ref_numpy
+    out = np.empty((len(row_ids), n), dtype)
+    for j, r in enumerate(row_ids):
+        r = int(r)
+        if kind == "laplace3d":
+            rv, rc, rr, _ = gen.laplacian(prm["g"], prm["g"], prm["g"], r, r + 1, dtype)
+        elif kind == "laplace2d":
+            rv, rc, rr, _ = gen.laplacian(prm["g"], prm["g"], 1, r, r + 1, dtype)
+        elif kind == "band":
+            rv, rc, rr, _ = gen.band(prm["n"], prm["hb"], r, r + 1, dtype)
+        else:   # R-MAT: rows of the downloaded matrix
+            v, ci, ri = a_host
+            s, e = int(ri[r]), int(ri[r + 1])
+            rv, rc, rr = v[s:e], ci[s:e], np.array([0, e - s], np.uint64)
+        k_total = {"laplace3d": lambda: prm["g"] ** 3, "laplace2d": lambda: prm["g"] ** 2, "band": lambda: prm["n"]}.get(kind, lambda: 1 << prm["scale"])()
+        uniq, inv = np.unique(rc.astype(np.int64), return_inverse=True)
+        bsub = gen.dense_rows(k_total, n, B_SEED, gen.MODE_EXACT, 0.0, dtype, row_ids=uniq)
+        out[j] = ref_numpy.mul_dense_rowmajor(rv, inv.astype(np.uint64), rr, bsub)[0] if len(rc) else 0
+    return out
+
+
+def bitwise_equal(a, b):
+    a = np.where(a == 0, 0.0, a).astype(a.dtype)   # -0.0 == 0.0 to the reference (both dropped by insert)
+    b = np.where(b == 0, 0.0, b).astype(b.dtype)
+    return bool(np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8)))
+
+
+def csr_rows_dense(v, ci, ri, row_ids, r_base, n, dtype):
+    """Densify rows of a result Csr (reference layout) — zeros where insert dropped the value."""
+    out = np.zeros((len(row_ids), n), dtype)
+    for j, r in enumerate(row_ids):
+        s, e = int(ri[r - r_base]), int(ri[r - r_base + 1])
+        out[j, ci[s:e].astype(np.int64)] = v[s:e]
+    return out
+
+
 def sample_dense_rows(gpu, dense, row_ids):
     """Download selected rows of a device-resident dense matrix (one-row borrowed views)."""
     i = dense.info()
@@ -256,7 +350,7 @@ def run_config1(torch, gpu, peak, e=900_000):
     for h in (A, B, C):
         h.close()
     return {"workload": f"bench_as_written_e{e}_n10_f64", "rows": 1000, "nnz": nnz, "n": 10, "dtype": "f64",
-            "algo": {2: "merge", 3: "rowblock"}.get(info["algo"], "vector"), "ms_per_step": round(total_ms / 20, 4), "ms_best": round(min(per), 4),
+            "algo": ALGO_NAME.get(info["algo"], "?"), "ms_per_step": round(total_ms / 20, 4), "ms_best": round(min(per), 4),
             "gflops": round(2.0 * nnz * 10 / (total_ms / 20 * 1e-3) / 1e9, 2), "kernels_per_step": info["kernels"],
             "host_call_ms": round(t_host * 1e3, 3), "host_call_gflops": round(2.0 * nnz * 10 / t_host / 1e9, 3),
             "cpu_port_ms_full": round(t_cpu * 1e3, 3), "cpu_port_gflops": round(2.0 * nnz * 10 / t_cpu / 1e9, 4),
@@ -264,7 +358,7 @@ def run_config1(torch, gpu, peak, e=900_000):
             "note": "launch-bound on the GPU (11 MB of operands); the one config the CPU port runs in full"}
 
 
-def run_extra(torch, gpu, name, steps, warmup, peak):
+def run_extra(torch, gpu, name, steps, warmup, peak, tuning=None, label=None):
     """Secondary single-GPU workloads (kernel-only numbers, reported under other_workloads)."""
     from basic_sparse_matrix_b200 import gen
     kind, prm, n, dt = WORKLOADS[name]
@@ -274,12 +368,12 @@ def run_extra(torch, gpu, name, steps, warmup, peak):
     ai = A.info()
     B = gpu.DeviceDense.generate(ai["cols"], n, seed=4, mode=gen.MODE_EXACT, dtype=dtype)
     C = gpu.DeviceDense.alloc(ai["rows"], n, dtype)
-    total_ms, per = time_device_steps(torch, A, B, C, steps, warmup)
+    total_ms, per = time_device_steps(torch, A, B, C, steps, warmup, tuning)
     info = gpu.last_launch_info()
     t = total_ms / steps * 1e-3
     bm = bytes_min(ai["rows"], ai["nnz"], ai["cols"], n, s)
-    out = {"workload": name, "rows": ai["rows"], "nnz": ai["nnz"], "n": n, "dtype": dt,
-           "algo": {2: "merge", 3: "rowblock"}.get(info["algo"], "vector"), "ms_per_step": round(total_ms / steps, 4),
+    out = {"workload": label or name, "rows": ai["rows"], "nnz": ai["nnz"], "n": n, "dtype": dt,
+           "algo": ALGO_NAME.get(info["algo"], "?"), "ms_per_step": round(total_ms / steps, 4),
            "ms_best": round(min(per), 4), "gflops": round(2.0 * ai["nnz"] * n / t / 1e9, 1),
            "eff_gbs": round(bm / t / 1e9, 1), "roofline_frac": round(bm / t / 1e9 / peak, 4),
            "kernels_per_step": info["kernels"]}
@@ -389,6 +483,27 @@ def main_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# the workloads reported under other_workloads at N=1 (the rest of WORKLOADS is for tools/sweep.py)
+EXTRAS = ["laplace2d_2048_n1_f64", "rmat20_n64_f64", "rmat20_n64_f32", "band_1m_hb32_n32_f32", "band_1m_hb32_n1_f32",
+          "laplace3d_256_n16_f64", "laplace3d_256_n8_f64", "laplace3d_256_n4_f64", "laplace3d_256_n1_f64",
+          "laplace3d_252_n128_f64", "laplace2d_4096_n64_f64"]
+
+
+def pinned(torch, shape, np_dtype):
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.uint64): torch.int64}[np.dtype(np_dtype)]
+    return torch.empty(shape, dtype=tdt).pin_memory().numpy().view(np_dtype)
+
+
+def mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -400,7 +515,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--gather", action="store_true", help="also time the optional NCCL all-gather of C row blocks")
+    ap.add_argument("--no-gather", action="store_true", help="skip the gathered result (NCCL all-gather of C row blocks and the fused scatter) at N > 1")
+    ap.add_argument("--gather", action="store_true", help="(default at N > 1; kept for compatibility)")
+    ap.add_argument("--no-target", action="store_true", help="skip the north_star target case (x64) in the same run")
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--tune", default="", help="k=v,k=v overrides of bsm_tuning (sweeps)")
     args = ap.parse_args()
@@ -411,7 +528,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from basic_sparse_matrix_b200 import Dense, gen, gpu
+    from basic_sparse_matrix_b200 import Csr, Dense, gen, gpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -419,6 +536,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     barrier = (lambda: dist.barrier()) if world > 1 else None
@@ -430,6 +548,18 @@ def main():
     torch.cuda.set_stream(stream)
     peak, peak_src = load_peaks()
 
+    def all_true(flag):
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     kind, prm, n, dt = WORKLOADS[args.workload]
     dtype = NP_DTYPE[dt]
     s = np.dtype(dtype).itemsize
@@ -440,6 +570,7 @@ def main():
 
     # ---- operands: nnz-balanced row block of A on this rank, B replicated ---------------------
     ri_full = host_row_index(kind, prm)
+    a_host = None
     if ri_full is not None:
         rows_total, nnz_total = len(ri_full) - 1, int(ri_full[-1])
         bounds = gpu.partition_rows(ri_full, world).astype(np.int64)
@@ -452,13 +583,14 @@ def main():
         rows_total, nnz_total = A.info()["rows"], A.info()["nnz"]
         bounds = np.array([0, rows_total], np.int64)
         r0, r1 = 0, rows_total
+        a_host = A.to_host().raw_parts()
     ai = A.info()
-    B = gpu.DeviceDense.generate(ai["cols"], n, seed=5, mode=gen.MODE_EXACT, dtype=dtype)
+    reach = {"laplace3d": lambda: prm["g"] ** 2, "laplace2d": lambda: prm["g"], "band": lambda: prm["hb"]}.get(kind, lambda: 0)()
+    B = gpu.DeviceDense.generate(ai["cols"], n, seed=B_SEED, mode=gen.MODE_EXACT, dtype=dtype)
     C = gpu.DeviceDense.alloc(ai["rows"], n, dtype)
 
     # ---- device-resident timing --------------------------------------------------------------------
     sampler = ClockSampler(local)
-    launches0 = gpu.kernel_launch_count()
     for _ in range(args.warmup):
         A.mul_dense(B, out=C, tuning=tuning)
     torch.cuda.synchronize()
@@ -480,140 +612,219 @@ def main():
     info = gpu.last_launch_info()
     total_ms = evs[0].elapsed_time(evs[-1])
     per = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
+    total_ms_max = max_over_ranks(total_ms)
     t_step = total_ms_max / args.steps * 1e-3
     value = 2.0 * nnz_total * n / t_step / 1e9
+
+    # ---- parity of THIS run's result, on every rank: sampled rows of the rank's own C block against the CPU oracle ----
+    ids = parity_row_ids(r0, r1, 64, reach)
+    got = sample_dense_rows(gpu, C, ids - r0)
+    ok_local = bitwise_equal(got, oracle_rows(kind, prm, n, dtype, ids, a_host))
+    parity = {"rows_checked": int(len(ids)) * world, "bitwise": all_true(ok_local), "checker": "CPU oracle (oracle/ref_numpy.py: sequential sum in "
+              "stored order, mul then add — src/sparse.rs:431-444) on rows of every rank's device-resident C block: first / last rows, "
+              "rows one stencil reach inside the block, hashed rows", "ranks": world}
 
     # roofline of the dominant kernel on this rank (per launch)
     kref = k_ref_of(kind, prm, rows_total, r0, r1)
     bm_rank = bytes_min(ai["rows"], ai["nnz"], kref, n, s)
     t_launch = total_ms / args.steps * 1e-3 / max(1, info["passes"])
     achieved = bm_rank / max(1, info["passes"]) / t_launch / 1e9 if info["passes"] else 0.0
-    traffic = None
+    # DRAM traffic of the kernel from the committed ncu capture — only if it is a capture of THIS launch configuration
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
-            traffic = json.load(open(tp)).get(args.workload if world == 1 else "", None)
+            ent = json.load(open(tp)).get(args.workload)
+            sig = {k: info[k] for k in ("algo", "lanes_per_row", "reg_tiles", "reg_flavour", "b_prefetch", "rows_per_warp")}
+            if isinstance(ent, dict) and ent.get("launch") == sig:
+                traffic, traffic_src = ent.get("dram_bytes"), ent.get("source")
         except Exception:
             traffic = None
     bm_total = bytes_min(rows_total, nnz_total, rows_total, n, s)
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic,
-                "kernel": ("spmm_rows_kernel" if info["algo"] == 1 else "spmm_merge_kernel"),
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": KERNEL_NAME.get(info["algo"], "?"),
                 "algorithmic_bytes_per_launch": int(bm_rank / max(1, info["passes"])),
                 "launch_ms_avg": round(t_launch * 1e3, 4), "launch_ms_best": round(min(per) / max(1, info["passes"]), 4),
                 "peak_source": peak_src}
 
-    # ---- optional gathered result (the only collective of the path) ---------------------------------
+    # ---- the gathered result (the only collective of the path; optional for callers, always measured here at N > 1) ----
     gather = None
-    if args.gather and world > 1:
-        uid = [gpu.Comm.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        comm = gpu.Comm.init(uid[0], world, rank)
-        full = gpu.DeviceDense.alloc(rows_total, n, dtype)
-        comm.allgather_rows(C, bounds.astype(np.uint64), full)       # warm-up (NCCL channel setup)
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        comm.allgather_rows(C, bounds.astype(np.uint64), full)
-        e1.record()
-        torch.cuda.synchronize()
-        g_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
-        gather = {"allgather_ms": round(float(g_ms.item()), 3), "bytes_received_per_gpu": int((rows_total - ai["rows"]) * n * s)}
-        # the same gathered product WITHOUT the collective: the SpMM kernel stores every C row into every
-        # rank's full buffer (peer memory over NVLink, mapped with CUDA IPC): multiply + gather in one kernel
+    if world > 1 and not args.no_gather:
+        gather = {}
         try:
-            ids = np.unique(np.concatenate([np.linspace(0, rows_total - 1, 96).astype(np.int64), bounds[:-1], bounds[1:] - 1]))
-            ref_rows = sample_dense_rows(gpu, full, ids)          # from the NCCL all-gather above
-            fi = full.info()
-            handles = [None] * world
-            dist.all_gather_object(handles, full.ipc_export())
-            peers = [gpu.DeviceDense.ipc_open(handles[r], rows_total, n, fi["ld"], dtype) for r in range(world) if r != rank]
-            dests = [full] + peers
+            uid = [gpu.Comm.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            comm = gpu.Comm.init(uid[0], world, rank)
+            full = gpu.DeviceDense.alloc(rows_total, n, dtype)
+            comm.allgather_rows(C, bounds.astype(np.uint64), full)       # warm-up (NCCL channel setup)
             torch.cuda.synchronize()
             dist.barrier()
-            gpu.fill_zero(full)                                    # so that the check below sees only what the fused kernel wrote
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            comm.allgather_rows(C, bounds.astype(np.uint64), full)
+            e1.record()
             torch.cuda.synchronize()
-            dist.barrier()
-            A.mul_dense_scatter(B, dests, r0)                      # warm-up (maps peer pages)
-            comm.barrier()
-            torch.cuda.synchronize()
-            dist.barrier()
-            reps = 3
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(reps):
-                A.mul_dense_scatter(B, dests, r0)
+            g_ms = max_over_ranks(e0.elapsed_time(e1))
+            # rows of the GATHERED buffer against the oracle: a few rows of EVERY rank's block, not only this rank's
+            gids = np.unique(np.concatenate([parity_row_ids(int(bounds[q]), int(bounds[q + 1]), 12, reach) for q in range(world)]))
+            want_g = oracle_rows(kind, prm, n, dtype, gids, a_host)
+            ok_nccl = all_true(bitwise_equal(sample_dense_rows(gpu, full, gids), want_g))
+            gather.update({"allgather_ms": round(g_ms, 3), "bytes_received_per_gpu": int((rows_total - ai["rows"]) * n * s),
+                           "spmm_plus_allgather_ms": round(total_ms_max / args.steps + g_ms, 3),
+                           "allgather_parity": {"rows_checked": int(len(gids)), "bitwise": ok_nccl,
+                                                "checker": "CPU oracle on rows of every rank's block in every rank's gathered buffer"}})
+            # the same gathered product WITHOUT the collective: the SpMM kernel stores every C row into every
+            # rank's full buffer (peer memory over NVLink, mapped with CUDA IPC): multiply + gather in one kernel
+            try:
+                fi = full.info()
+                handles = [None] * world
+                dist.all_gather_object(handles, full.ipc_export())
+                peers = [gpu.DeviceDense.ipc_open(handles[q], rows_total, n, fi["ld"], dtype) for q in range(world) if q != rank]
+                dests = [full] + peers
+                torch.cuda.synchronize()
+                dist.barrier()
+                gpu.fill_zero(full)                                    # so that the check below sees only what the fused kernel wrote
+                torch.cuda.synchronize()
+                dist.barrier()
+                A.mul_dense_scatter(B, dests, r0)                      # warm-up (maps peer pages)
                 comm.barrier()
-            f1.record()
-            torch.cuda.synchronize()
-            f_ms = torch.tensor([f0.elapsed_time(f1) / reps], dtype=torch.float64, device="cuda")
-            dist.all_reduce(f_ms, op=dist.ReduceOp.MAX)
-            same = bool(np.array_equal(sample_dense_rows(gpu, full, ids).view(np.uint8), ref_rows.view(np.uint8)))
-            gather.update({"fused_scatter_ms": round(float(f_ms.item()), 3),
-                           "spmm_plus_allgather_ms": round(total_ms_max / args.steps + float(g_ms.item()), 3),
-                           "fused_matches_allgather_on_sampled_rows": same,
-                           "fused_path": "bsm_spmm_scatter: P2P stores of every C row to all ranks' full buffers (CUDA IPC), then a 4-byte NCCL barrier"})
-            dist.barrier()
-            for h in peers:
-                h.close()
+                torch.cuda.synchronize()
+                dist.barrier()
+                reps = 3
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(reps):
+                    A.mul_dense_scatter(B, dests, r0)
+                    comm.barrier()
+                f1.record()
+                torch.cuda.synchronize()
+                f_ms = max_over_ranks(f0.elapsed_time(f1) / reps)
+                ok_fused = all_true(bitwise_equal(sample_dense_rows(gpu, full, gids), want_g))
+                gather.update({"fused_scatter_ms": round(f_ms, 3),
+                               "fused_parity": {"rows_checked": int(len(gids)), "bitwise": ok_fused,
+                                                "checker": "CPU oracle; the buffer was zeroed before the fused kernel ran"},
+                               "fused_path": "bsm_spmm_scatter: P2P stores of every C row to all ranks' full buffers (CUDA IPC), then a 4-byte NCCL barrier"})
+                dist.barrier()
+                for h in peers:
+                    h.close()
+            except Exception as ex:
+                gather["fused_scatter_error"] = str(ex)[:300]
+            full.close()
+            comm.close()
         except Exception as ex:
-            gather["fused_scatter_error"] = str(ex)[:300]
-        full.close()
-        comm.close()
+            gather["error"] = str(ex)[:300]
+
+    # ---- north_star target case in the same run: the same matrix x 64 columns, f64 (>= 100 M nnz x 64) ------------------
+    target = None
+    if not args.no_target and kind == "laplace3d" and dt == "f64" and n != 64:
+        try:
+            nt = 64
+            Bt = gpu.DeviceDense.generate(ai["cols"], nt, seed=B_SEED, mode=gen.MODE_EXACT, dtype=dtype)
+            Ct = gpu.DeviceDense.alloc(ai["rows"], nt, dtype)
+            t_ms, t_per = time_device_steps(torch, A, Bt, Ct, max(5, args.steps // 2), 3, None, barrier)
+            t_info = gpu.last_launch_info()
+            steps_t = max(5, args.steps // 2)
+            t_ms_max = max_over_ranks(t_ms) / steps_t
+            ok_t = all_true(bitwise_equal(sample_dense_rows(gpu, Ct, ids - r0), oracle_rows(kind, prm, nt, dtype, ids, a_host)))
+            bm_t = bytes_min(rows_total, nnz_total, rows_total, nt, s)
+            bm_t_rank = bytes_min(ai["rows"], ai["nnz"], kref, nt, s)
+            target = {"workload": f"laplace3d_{prm['g']}_n64_f64", "ncols": nt, "nnz": nnz_total, "ms_per_step": round(t_ms_max, 4),
+                      "gflops": round(2.0 * nnz_total * nt / (t_ms_max * 1e-3) / 1e9, 1),
+                      "roofline_frac": round(bm_t_rank / (t_ms / steps_t * 1e-3) / 1e9 / peak, 4),
+                      "roofline_frac_job": round(bm_t / (t_ms_max * 1e-3) / 1e9 / (peak * world), 4),
+                      "north_star_bar": ">= 0.60 of the HBM roofline on 1 GPU, >= 6x at 8 GPUs",
+                      "parity_bitwise": ok_t, "launch": {k: t_info[k] for k in ("algo", "lanes_per_row", "reg_tiles", "reg_flavour", "b_prefetch", "grid", "block")}}
+            Ct.close()
+            if world > 1:
+                # the same run's ONE-GPU time of the whole problem (rank 0, the others wait), for the speed-up
+                one_ms = 0.0
+                if rank == 0:
+                    A1 = make_device_csr(gpu, kind, prm, dtype)
+                    C1 = gpu.DeviceDense.alloc(rows_total, nt, dtype)
+                    o_ms, _ = time_device_steps(torch, A1, Bt, C1, steps_t, 3)
+                    one_ms = o_ms / steps_t
+                    A1.close()
+                    C1.close()
+                dist.barrier()
+                one_ms = max_over_ranks(one_ms)
+                target.update({"one_gpu_ms_same_run": round(one_ms, 4), "speedup_vs_one_gpu_same_run": round(one_ms / t_ms_max, 3)})
+            Bt.close()
+        except Exception as ex:
+            target = {"error": str(ex)[:300]}
 
     # ---- end to end through the reference-facing C-ABI calls, from pinned HOST buffers --------------------
-    e2e = None
+    e2e = e2e_dense = None
     host_cols = None
     if not args.no_e2e:
-        from basic_sparse_matrix_b200 import Csr
+        torch_dt = torch.float64 if dt == "f64" else torch.float32
         # host operands in the REFERENCE layout: Csr fields (usize indices) and Dense columns
         hA = A.to_host()                                    # rows [r0,r1) as a finalised Csr
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
         hv, hci, hri = (pin(x) for x in hA.raw_parts())
         hA = Csr.from_raw_parts((ai["rows"], ai["cols"]), hv, hci, hri)
-        host_cols = [torch.empty(ai["cols"], dtype=torch.float64 if dt == "f64" else torch.float32).pin_memory().numpy()
-                     for _ in range(n)]
+        host_cols = [torch.empty(ai["cols"], dtype=torch_dt).pin_memory().numpy() for _ in range(n)]
         B.to_host(Dense.from_columns_nocopy(host_cols))     # the host copy of B (outside the timed region)
-        out_cols = [torch.empty(ai["rows"], dtype=torch.float64 if dt == "f64" else torch.float32).pin_memory().numpy()
-                    for _ in range(n)]
-        hB, hC = Dense.from_columns_nocopy(host_cols), Dense.from_columns_nocopy(out_cols)
-        # the call uploads only the window of B rows this rank's A block references (all of B at N=1)
-        h2d = hv.nbytes + hci.nbytes + hri.nbytes + k_ref_of(kind, prm, rows_total, r0, r1) * n * s
-        d2h = sum(c.nbytes for c in out_cols)
+        hB = Dense.from_columns_nocopy(host_cols)
+        # the calls upload only the window of B rows this rank's A block references (all of B at N=1)
+        h2d = hv.nbytes + hci.nbytes + hri.nbytes + kref * n * s
+        chk_ids = parity_row_ids(r0, r1, 64, reach)
+        want_rows = oracle_rows(kind, prm, n, dtype, chk_ids, a_host)
 
-        def e2e_step():
-            # ONE reference-facing call: host Csr x host Dense -> host Dense. Inside: H2D of A (usize
-            # indices narrowed on the device), then per group of 32 columns H2D of B columns |
-            # transpose + SpMM + transpose | D2H of C columns, overlapped on three streams.
-            hA.mul_dense_into(hB, hC, algo=args.algo)
+        def timed(fn, steps):
+            gpu.phase_timers(enable=True)                   # reset
+            fn()                                            # warm-up (stream-ordered pool, pinned pages)
+            torch.cuda.synchronize()
+            gpu.phase_timers()                              # discard the warm-up's phases
+            if barrier:
+                barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            torch.cuda.synchronize()
+            te = (time.perf_counter() - t0) / steps
+            ph = {k: round(v / steps * 1e3, 2) for k, v in gpu.phase_timers(enable=False).items()}
+            return max_over_ranks(te), ph
 
-        e2e_step()                                          # warm-up
-        torch.cuda.synchronize()
-        if barrier:
-            barrier()
-        t0 = time.perf_counter()
-        for _ in range(max(1, args.e2e_steps)):
-            e2e_step()
-        torch.cuda.synchronize()
-        te = (time.perf_counter() - t0) / max(1, args.e2e_steps)
-        te_t = torch.tensor([te], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
-        te = float(te_t.item())
-        # result check of the e2e path against the device-resident product
-        chk = np.array_equal(out_cols[0][:1000], C.to_rowmajor()[:1000, 0]) if ai["rows"] >= 1000 else True
-        e2e = {"value": round(2.0 * nnz_total * n / te / 1e9, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": round(te * 1e3, 2), "steps": max(1, args.e2e_steps),
-               "matches_device_path": bool(chk),
-               "path": "Csr.mul_dense_into -> bsm_mul_dense_host_dense_f64: host Csr + host Dense columns in, host Dense columns out, "
-                       "column-group pipeline (H2D | transpose+SpMM+transpose | D2H), pinned host buffers"}
-        del out_cols
+        steps_e = max(1, args.e2e_steps)
+        # (1) dense result
+        out_cols = [torch.empty(ai["rows"], dtype=torch_dt).pin_memory().numpy() for _ in range(n)]
+        hC = Dense.from_columns_nocopy(out_cols)
+        te, ph = timed(lambda: hA.mul_dense_into(hB, hC, algo=args.algo), steps_e)
+        got_rows = np.stack([np.array([c[r - r0] for c in out_cols]) for r in chk_ids]).astype(dtype)
+        e2e_dense = {"value": round(2.0 * nnz_total * n / te / 1e9, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
+                     "d2h_bytes_per_step": int(sum(c.nbytes for c in out_cols)), "ms_per_step": round(te * 1e3, 2), "steps": steps_e,
+                     "parity": {"rows_checked": int(len(chk_ids)) * world, "bitwise": all_true(bitwise_equal(got_rows, want_rows)), "checker": "CPU oracle"},
+                     "phases_ms_rank0": ph,
+                     "path": "Csr.mul_dense_into -> bsm_mul_dense_host_dense_*: host Csr + host Dense columns in, host Dense columns out (no zero-drop)"}
+        del out_cols, hC
+        # (2) the literal call: zero-dropped Csr result into pinned arrays sized for the worst case (every output non-zero)
+        cap = ai["rows"] * n
+        need_gb = cap * (s + 8) / 1e9
+        avail = mem_available_gb()
+        if avail is not None and need_gb > 0.8 * avail:
+            e2e = {"skipped": f"result arrays need {need_gb:.1f} GB of pinned host memory, {avail:.1f} GB available"}
+        else:
+            ov, oc, orow = pinned(torch, cap, dtype), pinned(torch, cap, np.uint64), pinned(torch, ai["rows"] + 1, np.uint64)
+            res = [None]
+
+            def step_csr():
+                res[0] = hA.mul_dense_csr_into(hB, ov, oc, orow, algo=args.algo)
+
+            te, ph = timed(step_csr, steps_e)
+            rv, rc, rr = res[0].raw_parts()
+            got_rows = csr_rows_dense(rv, rc, rr, chk_ids, r0, n, dtype)
+            nnz_out = int(rr[-1])
+            e2e = {"value": round(2.0 * nnz_total * n / te / 1e9, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(nnz_out * (s + 8) + (ai["rows"] + 1) * 8), "ms_per_step": round(te * 1e3, 2), "steps": steps_e,
+                   "result": "Csr (zero-dropped, usize indices) — the reference's return type", "result_nnz_rank0": nnz_out,
+                   "parity": {"rows_checked": int(len(chk_ids)) * world, "bitwise": all_true(bitwise_equal(got_rows, want_rows)),
+                              "checker": "CPU oracle; rows of the returned Csr densified (dropped zeros = 0)"},
+                   "phases_ms_rank0": ph, "numa": numa,
+                   "path": "Csr.mul_dense_csr_into -> bsm_mul_dense_host_into_*: the literal Csr::mul_dense (sparse.rs:426-446): host Csr + host Dense "
+                           "columns in, zero-dropped host Csr out; pipeline = A up | B up in row chunks + transpose | per row block SpMM + count/scan/scatter | "
+                           "values + usize columns + row_index down; pinned host buffers"}
+            del ov, oc, orow, res
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's CPU path on a bounded sample ------------------
     cpu = None
@@ -632,13 +843,19 @@ def main():
     host_cols = None
     extras = []
     if rank == 0 and world == 1 and not args.no_extras:
-        for name in WORKLOADS:
+        for name in EXTRAS:
             if name == args.workload:
                 continue
             try:
                 extras.append(run_extra(torch, gpu, name, 10, 3, peak))
             except Exception as ex:   # keep the headline line even if a side workload fails
                 extras.append({"workload": name, "error": str(ex)[:200]})
+        try:   # config 5's product with the OPT-IN fused arithmetic (tolerance-level agreement), next to the bit-exact default above
+            from basic_sparse_matrix_b200 import _lib
+            fused = gpu.make_tuning("auto", flags=_lib.TUNE_A_EVICT_FIRST | _lib.TUNE_C_STREAMING | _lib.TUNE_FUSED)
+            extras.append(run_extra(torch, gpu, "band_1m_hb32_n32_f32", 10, 3, peak, fused, "band_1m_hb32_n32_f32 [BSM_TUNE_FUSED opt-in]"))
+        except Exception as ex:
+            extras.append({"workload": "band_1m_hb32_n32_f32 [BSM_TUNE_FUSED opt-in]", "error": str(ex)[:200]})
         try:
             extras.append(run_config1(torch, gpu, peak))
         except Exception as ex:
@@ -651,10 +868,11 @@ def main():
                 "config": {"workload": args.workload, "rows": rows_total, "nnz": nnz_total, "ncols": n,
                            "partition": f"nnz-balanced row blocks x{world}, B replicated, no data-path collective",
                            "l2": "operands >> L2 (126 MB), no flush needed", "values": "exact dyadic (k/1024), hash-generated on device",
-                           "algo": "vector" if info["algo"] == 1 else "merge", "launch": info},
+                           "algo": ALGO_NAME.get(info["algo"], "?"), "launch": info},
+                "parity": parity, "north_star_target": target,
                 "effective_gbs": round(bm_total / t_step / 1e9, 1),
                 "roofline_frac_job": round(bm_total / t_step / 1e9 / (peak * world), 4),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense": e2e_dense, "gpu_launches": int(launches), "clocks": clocks,
                 "ms_per_step_best": round(min(per), 4), "gather": gather, "other_workloads": extras}
         print(json.dumps(line))
     if world > 1:

@@ -226,6 +226,20 @@ int bsm_dense_to_csr(const bsm_dense *d, bsm_csr **out);
  * device-resident dense matrices of equal shape, accumulated in f64 with a fixed reduction tree. */
 int bsm_dense_residual_norm(const bsm_dense *ax, const bsm_dense *b, double *resid_fro, double *b_fro);
 
+/* The two substitutions of the reference's `solve` (src/lib.rs:11-24), on the device, for device-resident operands:
+ *   bsm_forward_substitution  = forward_substitution(l, b)        lib.rs:28-46   L y = b, rows ascending:
+ *       l_x = sum, in stored order, of v * y[col] over the stored entries of row r whose column != r;
+ *       y[r] = (b[r] - l_x) / (last stored entry of row r);
+ *   bsm_backward_substitution = backward_substitution(l_star, y)  lib.rs:49-65   L* x = y, rows descending:
+ *       the first stored entry of a row is skipped, x[r] = (y[r] - l_x) / (first stored entry of row r).
+ * Every product and sum is rounded separately, in the reference's order -> bit-identical to the reference for any data
+ * (the reference is f32 only; f64 is offered with the same semantics). One lane per right-hand-side column, rows in
+ * sequence: latency-bound by construction. l must be square with rows(l) == rows(b); y / x: rows(b) x cols(b), distinct
+ * from b. A row without a stored entry (the reference panics there) -> BSM_ERR_INVALID_ARGUMENT. The factorisation itself
+ * (Csr::cholesky_decomp, sparse.rs:682-714, and transpose) is out of scope and stays with the caller. */
+int bsm_forward_substitution(const bsm_csr *l, const bsm_dense *b, bsm_dense *y);
+int bsm_backward_substitution(const bsm_csr *l_star, const bsm_dense *y, bsm_dense *x);
+
 /* Host-to-host convenience = the literal reference call: uploads A and B, multiplies, compacts
  * and returns the zero-dropped result Csr in reference layout. The result arrays are allocated
  * by the library; release with bsm_host_free. */

@@ -97,3 +97,65 @@ def solve_band(a_band: np.ndarray, b_cols: np.ndarray) -> np.ndarray:
     L.osolve_band_f32.argtypes = [C.c_size_t, C.c_size_t, _F, C.c_size_t, _F, _F, _F, _F]
     assert L.osolve_band_f32(n, w - 1, _p(a_band), nrhs, _p(b_cols), _p(x), _p(l_band), _p(y)) == 0
     return x
+
+
+# ---- generic CSR restatements (small cases; pure Python loops over the reference's own statements) ----------------------
+def forward_csr(v, ci, ri, b_cols):
+    """lib.rs:28-46 on a Csr given by its raw parts; b_cols is (nrhs, n), one row per Dense column. f32 or f64."""
+    dt = v.dtype.type
+    nrhs, n = b_cols.shape
+    y = np.zeros_like(b_cols)
+    for c in range(nrhs):                                       # :32
+        for r in range(n):                                      # :33
+            l_x = dt(0.0)                                       # :35
+            s, e = int(ri[r]), int(ri[r + 1])
+            for k in range(s, e):                               # :37
+                if int(ci[k]) != r:                             # :38
+                    l_x = dt(l_x + dt(v[k] * y[c, int(ci[k])]))  # :39
+            y[c, r] = dt(dt(b_cols[c, r] - l_x) / v[e - 1])     # :42  row.last()
+    return y
+
+
+def backward_csr(v, ci, ri, y_cols):
+    """lib.rs:49-65 on a Csr (l_star) given by its raw parts."""
+    dt = v.dtype.type
+    nrhs, n = y_cols.shape
+    x = np.zeros_like(y_cols)
+    for c in range(nrhs):                                       # :53
+        for r in range(n - 1, -1, -1):                          # :54
+            l_x = dt(0.0)                                       # :56
+            s, e = int(ri[r]), int(ri[r + 1])
+            for k in range(s + 1, e):                           # :57  skip(1)
+                l_x = dt(l_x + dt(v[k] * x[c, int(ci[k])]))     # :58
+            x[c, r] = dt(dt(y_cols[c, r] - l_x) / v[s])         # :60  row[0]
+    return x
+
+
+def band_to_csr_lower(l_band: np.ndarray):
+    """Csr raw parts of the lower-triangular factor held in band storage: what `l.insert` builds in cholesky_decomp
+    (sparse.rs:710 -> 229: zeros are not stored), rows ascending, columns ascending (diagonal last)."""
+    n, w = l_band.shape
+    hb = w - 1
+    i = np.arange(n)[:, None]
+    j = i - hb + np.arange(w)[None, :]
+    keep = (j >= 0) & (l_band != 0)
+    ri = np.zeros(n + 1, np.uint64)
+    np.cumsum(keep.sum(axis=1), out=ri[1:])
+    return l_band[keep].astype(l_band.dtype), j[keep].astype(np.uint64), ri
+
+
+def band_to_csr_upper(l_band: np.ndarray):
+    """Csr raw parts of l.transpose() (sparse.rs:296-318): row r holds L[j][r] for j = r .. r+hb, columns ascending
+    (diagonal first), zeros not stored."""
+    n, w = l_band.shape
+    hb = w - 1
+    # element (r, j) of the transpose = L[j][r] = band[j, r - j + hb], j in [r, r + hb]
+    r = np.arange(n)[:, None]
+    j = r + np.arange(w)[None, :]
+    ok = j < n
+    jj = np.where(ok, j, 0)
+    vals = np.where(ok, l_band[jj, (r - jj + hb) % w], 0)
+    keep = ok & (vals != 0)
+    ri = np.zeros(n + 1, np.uint64)
+    np.cumsum(keep.sum(axis=1), out=ri[1:])
+    return vals[keep].astype(l_band.dtype), j[keep].astype(np.uint64), ri

@@ -287,14 +287,15 @@ def test_merge_within_tolerance_on_real_inputs(gpu, dtype, n):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_merge_grouped_lanes(gpu, dtype):
-    """merge-path with lanes_per_row < 32 and 2 or 4 register tiles per lane (32/G chunks side by side per warp):
-    bit-exact on exactly representable data, within tolerance on real data."""
+    """merge-path with lanes_per_row < 32 and 2 register tiles per lane (32/G chunks side by side per warp):
+    bit-exact on exactly representable data, within tolerance on real data. (The 4-tile and 4-lane variants of round 1
+    never won a sweep and are no longer built.)"""
     rng = np.random.default_rng(404)
     m, k = 1500, 600
     per16 = 16 // np.dtype(dtype).itemsize
     ve, cie, rie = random_csr(rng, m, k, dtype, mean_len=4, empty_frac=0.4, giant_row=777, giant_len=9000, exact=True)
     vr, cir, rir = random_csr(rng, m, k, dtype, mean_len=6, giant_row=1, giant_len=5000)
-    for g, nt in ((16, 2), (8, 4), (8, 2), (4, 4), (16, 4), (4, 2)):
+    for g, nt in ((16, 2), (8, 2)):
         n = per16 * g * nt
         be = random_dense(rng, k, n, dtype, exact=True)
         for tune in (dict(), dict(merge_items=96), dict(merge_items=32, warps_per_cta=4)):
@@ -320,14 +321,23 @@ def test_merge_items_variants(gpu):
 
 
 def test_merge_is_deterministic(gpu):
+    """A hub row of 20 000 entries with the DEFAULT items per chunk: more than 64 carrying chunks, so the long-run fix-up
+    kernel (merge_fixup_long_kernel) sums it. Run-to-run identical, and against the oracle: within the stated tolerance on
+    real data, bit-exact on dyadic data."""
     rng = np.random.default_rng(23)
     m, k, n = 800, 500, 64
     v, ci, ri = random_csr(rng, m, k, np.float64, giant_row=10, giant_len=20_000)
     b = random_dense(rng, k, n, np.float64)
-    first, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
+    first, info = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
+    assert info["kernels"] >= 3 and (20_000 + 11) // info["merge_items"] > 64, info   # merge + both fix-up kernels
     for _ in range(3):
         again, _ = gpu_product(gpu, (m, k), v, ci, ri, b, "merge")
         assert_bitwise(again, first, "run-to-run")
+    assert_tolerance(first, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), ref_numpy.abs_product_sum(v, ci, ri, b), 1e-12, "long-run fix-up vs oracle")
+    ve, cie, rie = random_csr(rng, m, k, np.float64, giant_row=10, giant_len=20_000, exact=True)
+    be = random_dense(rng, k, n, np.float64, exact=True)
+    got, _ = gpu_product(gpu, (m, k), ve, cie, rie, be, "merge")
+    assert_bitwise(got, ref_numpy.mul_dense_rowmajor(ve, cie, rie, be), "long-run fix-up, exact data")
 
 
 # ---- edge shapes (SURVEY §4.2) ----------------------------------------------------------------------------
@@ -444,7 +454,7 @@ def test_device_generators_match_numpy(gpu, dtype):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [1, 5, 32, 33, 100])
 def test_pipelined_host_to_host_dense_product(gpu, dtype, n):
-    """bsm_mul_dense_host_dense_*: column-group pipeline (H2D | multiply | D2H) == the oracle, bit for bit."""
+    """bsm_mul_dense_host_dense_*: the pipelined host-to-host product with a dense result == the oracle, bit for bit."""
     rng = np.random.default_rng(21)
     m, k = 777, 501
     v, ci, ri = random_csr(rng, m, k, dtype, mean_len=7)
@@ -455,6 +465,57 @@ def test_pipelined_host_to_host_dense_product(gpu, dtype, n):
     with pytest.raises(MatError) as e:
         a.mul_dense_into(Dense.new_default_with_dims(2, k + 1, dtype))
     assert e.value.kind == MatErr.IncorrectDimensions
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kind", ["random", "band", "hub"])
+def test_pipelined_literal_call_many_blocks_and_chunks(gpu, dtype, kind, monkeypatch):
+    """bsm_mul_dense_host_into_* and bsm_mul_dense_host_dense_* with the pipeline's block / chunk sizes shrunk so that a small
+    product runs through dozens of row blocks and B chunks (views of A, windows of B, per-block compaction, the lagged
+    device->host copies): the result Csr must equal the oracle's field by field, the dense twin bit for bit."""
+    monkeypatch.setenv("BSM_PIPE_BLOCK_BYTES", "20000")
+    monkeypatch.setenv("BSM_PIPE_CHUNK_BYTES", "9000")
+    rng = np.random.default_rng(91)
+    m, k, n = 1501, 1203, 12
+    if kind == "band":
+        v, ci, ri = _runs_csr(rng, m, k, dtype, 30, band=True)
+        v = (np.round(v * 8) / 8).astype(dtype)
+        v[v == 0] = 0.125
+    elif kind == "hub":
+        v, ci, ri = random_csr(rng, m, k, dtype, mean_len=5, empty_frac=0.3, giant_row=700, giant_len=6000, exact=True)
+    else:
+        v, ci, ri = random_csr(rng, m, k, dtype, mean_len=7, exact=True)
+    b = random_dense(rng, k, n, dtype, exact=True)
+    b[:, 3] = 0                                   # a zero output column: dropped from every row of the result Csr
+    a = host_csr((m, k), v, ci, ri)
+    rhs = Dense.from_data([b[:, c] for c in range(n)], dtype)
+    ref = OracleCsr.from_raw((m, k), v, ci, ri).mul_dense([b[:, c].copy() for c in range(n)])
+    out = a.mul_dense(rhs)                        # allocating form
+    assert_bitwise(out.v, ref.v)
+    assert np.array_equal(out.col_index, ref.col_index) and np.array_equal(out.row_index, ref.row_index)
+    ov, oc, orow = np.empty(m * n, dtype), np.empty(m * n, np.uint64), np.empty(m + 1, np.uint64)
+    out2 = a.mul_dense_csr_into(rhs, ov, oc, orow)
+    assert out2 == out
+    with pytest.raises(_lib.BsmError):            # result arrays too small
+        a.mul_dense_csr_into(rhs, ov[:10], oc[:10], orow)
+    dense = a.mul_dense_into(rhs)
+    assert_bitwise(dense.to_rowmajor(), ref_numpy.mul_dense_rowmajor(v, ci, ri, b), f"dense twin {kind}")
+
+
+def test_literal_call_edge_shapes(gpu):
+    """Empty matrix, empty rows at both ends, one column, zero columns."""
+    for (m, k, n) in ((0, 5, 3), (7, 5, 0), (9, 4, 1), (3, 3, 2)):
+        a = Csr.new((m, k), np.float64)
+        if m >= 3:
+            a.insert(2.0, 1, 0)
+        a = a.finalise()
+        rhs = Dense.from_data([np.arange(1, k + 1, dtype=np.float64) for _ in range(n)]) if n else Dense(0, k, [])
+        out = a.mul_dense(rhs)
+        want = Csr.new((m, n), np.float64)
+        if m >= 3:
+            for c in range(n):
+                want.insert(2.0, 1, c)
+        assert out == want.finalise(), (m, k, n)
 
 
 @pytest.mark.parametrize("seed", range(6))
