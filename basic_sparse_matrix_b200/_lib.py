@@ -52,8 +52,7 @@ class Tuning(C.Structure):
         ("algo", C.c_int32), ("col_tile", C.c_int32), ("rows_per_slice", C.c_int32),
         ("stages", C.c_int32), ("warps_per_cta", C.c_int32), ("ctas_per_sm", C.c_int32),
         ("merge_items", C.c_int32), ("flags", C.c_uint32), ("rows_per_warp", C.c_int32),
-        ("prefer_wide_rows", C.c_int32), ("reg_flavour", C.c_int32), ("lanes_per_row", C.c_int32), ("b_prefetch", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("prefer_wide_rows", C.c_int32), ("reg_flavour", C.c_int32), ("lanes_per_row", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -64,7 +63,7 @@ class LaunchInfo(C.Structure):
         ("block", C.c_int32), ("smem_bytes", C.c_int32), ("rows_per_slice", C.c_int32),
         ("stages", C.c_int32), ("capacity", C.c_int32), ("passes", C.c_int32),
         ("merge_items", C.c_int32), ("merge_chunks", C.c_int32), ("rows_per_warp", C.c_int32),
-        ("reg_flavour", C.c_int32), ("col_tile", C.c_int32), ("b_prefetch", C.c_int32),
+        ("reg_flavour", C.c_int32), ("col_tile", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
     def as_dict(self):

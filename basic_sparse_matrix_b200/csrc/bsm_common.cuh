@@ -162,12 +162,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
-// L2 prefetch of a contiguous piece of global memory by the TMA unit (fire and forget; 16-byte aligned address and size)
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
-}
-
 // ---- per-lane column vectors -----------------------------------------------------------------
 template <typename T, int V> struct VecT;
 template <> struct VecT<double, 1> { using type = double; };

@@ -19,16 +19,6 @@ struct ScatterTargets {
     uint64_t row_offset = 0;
 };
 
-// Default L2 prefetch distance of the diagonal B rows, in rows (0 = none). Set from the same-box A/B sweeps in
-// profiles/r2_sweep_prefetch_*.jsonl.
-static int default_b_prefetch(const MatrixFacts &m, uint32_t n, size_t s)
-{
-    (void)m;
-    (void)n;
-    (void)s;
-    return 0;
-}
-
 static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning &tn, uint32_t flags, cudaStream_t stream,
                        const ScatterTargets *scatter = nullptr)
 {
@@ -64,20 +54,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         }
         VectorPlan plan;
         BSM_TRY(plan_vector_pass(m, dev, tn, n, PassAlign{b->ld, c->ld, col0, b->data, c->data}, scatter != nullptr, multi, &plan));
-        // L2 prefetch of the diagonal B rows (flat-stream shapes on stencil-like matrices whose B rows are 16-byte granular)
-        {
-            const bool flat = plan.sh.G == 32 || plan.sh.NT > 1;
-            const uint64_t row_bytes = (uint64_t)n * s, ldb_bytes = b->ld * s;
-            int dist = tn.b_prefetch;
-            if (dist == 0) dist = default_b_prefetch(m, n, s);
-            if (dist > 0 && flat && a->row_stride && row_bytes % 16 == 0 && ldb_bytes % 16 == 0 && ((uintptr_t)p.B % 16) == 0 &&
-                b->rows > a->row_offset && row_bytes >= 64) {
-                p.pf_rows = (uint32_t)dist;
-                p.pf_bytes = (uint32_t)row_bytes;
-                p.pf_limit = (uint32_t)std::min<uint64_t>(b->rows - a->row_offset, 0xFFFFFFF0ull);
-                p.pf_base = (const char *)p.B + (size_t)a->row_offset * ldb_bytes;
-            }
-        }
         const Shape sh = plan.sh;
         const int flavour = plan.flavour, nw = plan.nw;
         const size_t smem = plan.smem;
@@ -106,7 +82,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
             launch_info().reg_flavour = flavour + 1;
             launch_info().stages = (int)p.stages;
             launch_info().capacity = (int)p.cap;
-            launch_info().b_prefetch = (int)p.pf_rows;
         }
     }
     launch_info().passes = passes;

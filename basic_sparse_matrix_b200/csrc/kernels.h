@@ -28,10 +28,6 @@ struct RowParams {
     uint32_t cap;        // staged entries per slice (multiple of 4)
     uint32_t stages;     // TMA ring depth per warp
     uint32_t flags;      // BSM_TUNE_*
-    uint32_t pf_rows;    // L2 prefetch distance in rows (0 = off): the owner of row r prefetches B row (r + pf_rows) of its diagonal
-    uint32_t pf_bytes;   // bytes of one B row of this pass (multiple of 16)
-    uint32_t pf_limit;   // local rows r for which B row r exists
-    const char *pf_base; // B row of local row 0, first column of this pass (16-byte aligned)
     uint32_t n_peers;    // scatter variant: further destinations of every C row (0 = none)
     char *peers[7];      // their C pointers, offset like C (first column of the pass, this rank's first row)
 };

@@ -116,16 +116,24 @@ template <typename T> struct HostProduct {
     uint64_t *out_col_index, *out_row_index, *out_nnz;
 };
 
-constexpr uint64_t kBlockBytes = 256ull << 20;   // C rows per block: about this many bytes of row-major result
-constexpr uint64_t kChunkBytes = 128ull << 20;   // B rows per chunk
+// Granularity. A block of output rows / a chunk of B rows moves over PCIe as n column pieces (the reference's Dense is one Vec
+// per column), so the pieces must stay large: 1 MB pieces measured 30 GB/s host->device against 50 GB/s for contiguous
+// 256 MB copies (profiles/r2_e2e_phases.md). Blocks and chunks are therefore at most kMaxBytes of row-major data and at least
+// kMinPiece bytes per column piece, and in between an eighth of the operand so that a mid-size product still overlaps its copies.
+constexpr uint64_t kMaxBytes = 1ull << 30;
+constexpr uint64_t kMinPiece = 2ull << 20;
+static uint64_t pipe_rows(uint64_t total_rows, uint64_t row_bytes, uint64_t elem_bytes, uint64_t override_bytes)
+{
+    if (override_bytes) return std::max<uint64_t>(1, override_bytes / row_bytes);
+    const uint64_t hi = std::max<uint64_t>(1, kMaxBytes / row_bytes), lo = kMinPiece / elem_bytes;
+    return std::min(hi, std::max(lo, total_rows / 8));
+}
 // BSM_PIPE_BLOCK_BYTES / BSM_PIPE_CHUNK_BYTES override the two (the tests shrink them to drive many blocks and chunks
 // through small matrices)
-static uint64_t env_bytes(const char *name, uint64_t dflt)
+static uint64_t env_bytes(const char *name)
 {
     const char *e = getenv(name);
-    if (!e || !*e) return dflt;
-    const unsigned long long v = strtoull(e, nullptr, 10);
-    return v ? (uint64_t)v : dflt;
+    return (e && *e) ? (uint64_t)strtoull(e, nullptr, 10) : 0;
 }
 
 template <typename T> int host_product(const HostProduct<T> &q)
@@ -160,13 +168,13 @@ template <typename T> int host_product(const HostProduct<T> &q)
     DevTimeline tl;
     // geometry
     const uint64_t ld = default_ld(n, q.dtype);
-    uint64_t rb = std::max<uint64_t>(4, env_bytes("BSM_PIPE_BLOCK_BYTES", kBlockBytes) / (ld * s) / 4 * 4);       // rows per block (multiple of 4: the row_ptr
+    uint64_t rb = std::max<uint64_t>(4, pipe_rows(rows, ld * s, s, env_bytes("BSM_PIPE_BLOCK_BYTES")) / 4 * 4);       // rows per block (multiple of 4: the row_ptr
     if (a->row_stride && rb > a->row_stride) rb = rb / a->row_stride * a->row_stride;   // window of a view stays 16-byte
     if (rb % 4) rb = (rb + 3) / 4 * 4;                                           // aligned); whole stencil lines
     rb = std::min(rb, (rows + 3) / 4 * 4);
     if ((rows + rb - 1) / rb > 4096) rb = ((rows + 4095) / 4096 + 3) / 4 * 4;
     const uint32_t nblocks = (uint32_t)((rows + rb - 1) / rb);
-    const uint64_t cb = std::max<uint64_t>(32, env_bytes("BSM_PIPE_CHUNK_BYTES", kChunkBytes) / (n * s) / 32 * 32);   // B rows per chunk
+    const uint64_t cb = std::min<uint64_t>(round_up(q.rhs_rows, 32), std::max<uint64_t>(32, pipe_rows(q.rhs_rows, n * s, s, env_bytes("BSM_PIPE_CHUNK_BYTES")) / 32 * 32));   // B rows per chunk
     // window of B rows A references (a rank's row block of a banded / stencil matrix reads a window of B, not all of it)
     const bool has_entries = a->nnz != 0;
     const uint64_t win_lo = has_entries ? (uint64_t)a->col_min / 32 * 32 : 0;

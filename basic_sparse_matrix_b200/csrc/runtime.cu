@@ -254,8 +254,8 @@ int bsm_phase_timers_read(double *seconds, int count, int reset)
 
 const char *bsm_phase_name(int phase)
 {
-    static const char *names[PH_COUNT] = {"a_upload", "a_stats", "b_h2d_enqueue", "b_transpose_enqueue", "spmm_enqueue", "compact_enqueue",
-                                          "c_transpose_enqueue", "d2h_enqueue", "wait", "total"};
+    static const char *names[PH_COUNT] = {"a_upload_host", "a_stats_and_sync_host", "b_h2d_device", "b_transpose_device", "spmm_device", "compact_device",
+                                          "c_transpose_device", "d2h_device", "wait_host", "total_host"};
     return phase >= 0 && phase < PH_COUNT ? names[phase] : "";
 }
 

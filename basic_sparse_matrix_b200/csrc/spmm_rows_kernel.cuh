@@ -57,7 +57,7 @@ template <typename T, int V, int G, int NT, bool FULLN, int U, bool VECA, bool M
 __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t *__restrict__ rp, const uint32_t *__restrict__ ci,
                                               const T *__restrict__ va, uint32_t base, uint32_t row0, uint32_t nr,
                                               const char *__restrict__ b_bytes, char *__restrict__ c_bytes, const bool (&col_ok)[NT],
-                                              uint32_t grp, uint32_t gl, bool streaming, uint32_t lane_off)
+                                              uint32_t grp, bool streaming, uint32_t lane_off)
 {
     constexpr int RPP = 32 / G;
     const uint32_t ldb_bytes = p.ldb * (uint32_t)sizeof(T);
@@ -88,14 +88,6 @@ __device__ __forceinline__ void process_slice(const RowParams &p, const uint32_t
                             acc[t].store(reinterpret_cast<T *>(p.peers[d] + lane_off + crow) + t * G * V, false);
                 }
                 acc[t].zero();
-            }
-            // L2 prefetch of the B row this lane group's own row p.pf_rows rows ahead will read on the diagonal (stencil-like
-            // matrices): every B row is requested from DRAM once, by a fire-and-forget bulk prefetch, a few rows before its
-            // users (the rows one line / one plane away run on other warps and CTAs at about the same position) gather it,
-            // so the gathers are L2 hits and the in-order gather window no longer stalls on DRAM round trips
-            if (p.pf_rows && gl == 0) {
-                const uint32_t t = row0 + rr + p.pf_rows;
-                if (t < p.pf_limit) bulk_prefetch_l2(p.pf_base + (size_t)t * ldb_bytes, p.pf_bytes);
             }
             crow += ldc_bytes;
             ++rr;
@@ -238,9 +230,9 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
                 if constexpr (STAGED)
                     process_slice<T, V, G, NT, FULLN, U, VECA, MULTI>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                                 reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,
-                                                                c_bytes, col_ok, grp, gl, streaming, gl * V * (uint32_t)sizeof(T));
+                                                                c_bytes, col_ok, grp, streaming, gl * V * (uint32_t)sizeof(T));
                 else
-                    process_slice<T, V, G, NT, FULLN, U, false, MULTI>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, gl,
+                    process_slice<T, V, G, NT, FULLN, U, false, MULTI>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp,
                                                                        streaming, gl * V * (uint32_t)sizeof(T));
             }
         }
@@ -352,9 +344,9 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
                 if constexpr (STAGED)
                     process_slice<T, V, G, NT, FULLN, U, VECA, MULTI>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                                 reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,
-                                                                c_bytes, col_ok, grp, gl, streaming, gl * V * (uint32_t)sizeof(T));
+                                                                c_bytes, col_ok, grp, streaming, gl * V * (uint32_t)sizeof(T));
                 else
-                    process_slice<T, V, G, NT, FULLN, U, false, MULTI>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp, gl,
+                    process_slice<T, V, G, NT, FULLN, U, false, MULTI>(p, rp, p.col_idx, vals, 0u, row0, nr, b_bytes, c_bytes, col_ok, grp,
                                                                        streaming, gl * V * (uint32_t)sizeof(T));
             }
         }

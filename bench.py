@@ -635,7 +635,7 @@ def main():
     if os.path.exists(tp) and world == 1:
         try:
             ent = json.load(open(tp)).get(args.workload)
-            sig = {k: info[k] for k in ("algo", "lanes_per_row", "reg_tiles", "reg_flavour", "b_prefetch", "rows_per_warp")}
+            sig = {k: info[k] for k in ("algo", "lanes_per_row", "reg_tiles", "reg_flavour", "rows_per_warp")}
             if isinstance(ent, dict) and ent.get("launch") == sig:
                 traffic, traffic_src = ent.get("dram_bytes"), ent.get("source")
         except Exception:
@@ -734,7 +734,7 @@ def main():
                       "roofline_frac": round(bm_t_rank / (t_ms / steps_t * 1e-3) / 1e9 / peak, 4),
                       "roofline_frac_job": round(bm_t / (t_ms_max * 1e-3) / 1e9 / (peak * world), 4),
                       "north_star_bar": ">= 0.60 of the HBM roofline on 1 GPU, >= 6x at 8 GPUs",
-                      "parity_bitwise": ok_t, "launch": {k: t_info[k] for k in ("algo", "lanes_per_row", "reg_tiles", "reg_flavour", "b_prefetch", "grid", "block")}}
+                      "parity_bitwise": ok_t, "launch": {k: t_info[k] for k in ("algo", "lanes_per_row", "reg_tiles", "reg_flavour", "grid", "block")}}
             Ct.close()
             if world > 1:
                 # the same run's ONE-GPU time of the whole problem (rank 0, the others wait), for the speed-up

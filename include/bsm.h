@@ -104,10 +104,7 @@ typedef struct bsm_tuning {
                                 Fewer lanes than the 128-bit loads need -> 2 or 4 register tiles per lane and
                                 32/lanes rows side by side, each lane group walking its own flat entry stream:
                                 one LDS of the A stream then feeds 32/lanes rows                            */
-    int32_t b_prefetch;      /* vector kernel on stencil-like matrices: the owner of row r asks the TMA unit to prefetch
-                                B row r + b_prefetch (the row its diagonal entry will read) into L2. 0 = heuristic,
-                                -1 = off                                                                            */
-    int32_t reserved[3];
+    int32_t reserved[4];
 } bsm_tuning;
 
 /* what the last bsm_spmm* call on this thread actually launched */
@@ -124,7 +121,7 @@ typedef struct bsm_launch_info {
     int32_t merge_items, merge_chunks;
     int32_t rows_per_warp, reg_flavour;
     int32_t col_tile;        /* columns of the FIRST pass (same meaning in bsm_spmm* and bsm_plan_vector)          */
-    int32_t b_prefetch;      /* rows of L2 prefetch distance the launch used (0 = none)                             */
+    int32_t reserved[1];
 } bsm_launch_info;
 
 /* ------------------------------------------------------------------------------------------

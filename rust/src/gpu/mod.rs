@@ -50,6 +50,10 @@ pub trait GpuScalar: Copy + Default + PartialEq + std::fmt::Debug {
     unsafe fn dense_upload(rows: u64, cols: u64, cols_ptr: *const *const Self, out: *mut *mut ffi::bsm_dense) -> i32;
     unsafe fn dense_download(d: *const ffi::bsm_dense, cols_ptr: *const *mut Self) -> i32;
     unsafe fn mul_vector(a: *const ffi::bsm_csr, rhs: *const Self, n: u64, out: *mut Self, m: u64) -> i32;
+    #[allow(clippy::too_many_arguments)]
+    unsafe fn mul_dense_host_into(rows: u64, cols: u64, nnz: u64, v: *const Self, ci: *const u64, ri: *const u64, ri_len: u64,
+                                  rhs_rows: u64, rhs_cols: u64, rhs_cols_ptr: *const *const Self, algo: i32, capacity: u64,
+                                  out_v: *mut Self, out_ci: *mut u64, out_ri: *mut u64, out_nnz: *mut u64) -> i32;
 }
 macro_rules! impl_scalar {
     ($t:ty, $code:expr, $up:ident, $down:ident, $dup:ident, $ddown:ident, $mv:ident) => {
@@ -61,11 +65,14 @@ macro_rules! impl_scalar {
             unsafe fn dense_upload(r: u64, c: u64, p: *const *const Self, o: *mut *mut ffi::bsm_dense) -> i32 { ffi::$dup(r, c, p, o) }
             unsafe fn dense_download(d: *const ffi::bsm_dense, p: *const *mut Self) -> i32 { ffi::$ddown(d, p) }
             unsafe fn mul_vector(a: *const ffi::bsm_csr, x: *const Self, n: u64, y: *mut Self, m: u64) -> i32 { ffi::$mv(a, x, n, y, m) }
+            unsafe fn mul_dense_host_into(r: u64, c: u64, n: u64, v: *const Self, ci: *const u64, ri: *const u64, l: u64, br: u64, bc: u64,
+                                          bp: *const *const Self, algo: i32, cap: u64, ov: *mut Self, oc: *mut u64, or: *mut u64,
+                                          on: *mut u64) -> i32 { ffi::$into(r, c, n, v, ci, ri, l, br, bc, bp, algo, cap, ov, oc, or, on) }
         }
     };
 }
-impl_scalar!(f64, ffi::BSM_F64, bsm_csr_upload_f64, bsm_csr_download_f64, bsm_dense_upload_f64, bsm_dense_download_f64, bsm_mul_vector_f64);
-impl_scalar!(f32, ffi::BSM_F32, bsm_csr_upload_f32, bsm_csr_download_f32, bsm_dense_upload_f32, bsm_dense_download_f32, bsm_mul_vector_f32);
+impl_scalar!(f64, ffi::BSM_F64, bsm_csr_upload_f64, bsm_csr_download_f64, bsm_dense_upload_f64, bsm_dense_download_f64, bsm_mul_vector_f64, bsm_mul_dense_host_into_f64);
+impl_scalar!(f32, ffi::BSM_F32, bsm_csr_upload_f32, bsm_csr_download_f32, bsm_dense_upload_f32, bsm_dense_download_f32, bsm_mul_vector_f32, bsm_mul_dense_host_into_f32);
 
 #[derive(Clone, Copy, Debug, PartialEq)]
 pub enum Algo { Auto = 0, VectorCsr = 1, MergePath = 2, RowBlock = 3 }
@@ -147,13 +154,44 @@ impl<T: GpuScalar> DeviceDense<T> {
     }
 }
 
-/// The literal drop-in for `Csr::mul_dense(&self, rhs:&Dense<T>) -> Result<Csr<T>,MatErr>`.
+/// The literal drop-in for `Csr::mul_dense(&self, rhs:&Dense<T>) -> Result<Csr<T>,MatErr>` (sparse.rs:426-446): host Csr and
+/// host Dense in, zero-dropped finalised host Csr out, through ONE pipelined C-ABI call (`bsm_mul_dense_host_into_*`: B up
+/// in row chunks, SpMM + result construction per block of rows, values / usize columns / row_index down, overlapped).
+/// The result Vecs are sized for the worst case (every output non-zero; untouched capacity costs no pages) and trimmed.
 impl<T: GpuScalar> Csr<T> {
     pub fn mul_dense_gpu(&self, rhs: &Dense<T>) -> Result<Csr<T>, GpuError> {
-        if self.get_dims().cols != rhs.get_dims().rows { return Err(GpuError::Mat(MatErr::IncorrectDimensions)); }
-        let a = DeviceCsr::from_host(self)?;
-        let b = DeviceDense::from_host(rhs)?;
-        a.mul_dense(&b)?.into_csr()?.to_host()
+        let (a, b) = (self.get_dims(), rhs.get_dims());
+        if a.cols != b.rows { return Err(GpuError::Mat(MatErr::IncorrectDimensions)); }          // sparse.rs:427-429
+        if !self.is_finalised() { return Err(GpuError::Mat(MatErr::MatrixNotFinalised)); }
+        let (v, ci, ri) = self.raw_parts();
+        let cols: Vec<*const T> = rhs.columns().iter().map(|c| c.as_ptr()).collect();
+        let cap = a.rows * b.cols;
+        let (mut ov, mut oc, mut or) = (Vec::<T>::with_capacity(cap), Vec::<usize>::with_capacity(cap), vec![0usize; a.rows + 1]);
+        let mut nnz = 0u64;
+        check(unsafe { T::mul_dense_host_into(a.rows as u64, a.cols as u64, v.len() as u64, v.as_ptr(), ci.as_ptr() as *const u64,
+                                              ri.as_ptr() as *const u64, ri.len() as u64, b.rows as u64, b.cols as u64, cols.as_ptr(),
+                                              Algo::Auto as i32, cap as u64, ov.as_mut_ptr(), oc.as_mut_ptr() as *mut u64,
+                                              or.as_mut_ptr() as *mut u64, &mut nnz) })?;
+        unsafe { ov.set_len(nnz as usize); oc.set_len(nnz as usize); }
+        ov.shrink_to_fit();
+        oc.shrink_to_fit();
+        Ok(Csr::from_raw_parts((a.rows, b.cols), ov, oc, or))
+    }
+}
+
+/// The substitution half of `solve` (lib.rs:11-24) on device-resident operands: `forward_substitution(l, b)` (lib.rs:28-46)
+/// and `backward_substitution(l_star, y)` (lib.rs:49-65), bit-identical to the reference's loops; the factorisation
+/// (`cholesky_decomp`, `transpose`) stays on the CPU.
+impl<T: GpuScalar> DeviceCsr<T> {
+    pub fn forward_substitution(&self, b: &DeviceDense<T>) -> Result<DeviceDense<T>, GpuError> {
+        let y = DeviceDense::<T>::alloc(b.dims.rows, b.dims.cols)?;
+        check(unsafe { ffi::bsm_forward_substitution(self.h, b.h, y.h) })?;
+        Ok(y)
+    }
+    pub fn backward_substitution(&self, y: &DeviceDense<T>) -> Result<DeviceDense<T>, GpuError> {
+        let x = DeviceDense::<T>::alloc(y.dims.rows, y.dims.cols)?;
+        check(unsafe { ffi::bsm_backward_substitution(self.h, y.h, x.h) })?;
+        Ok(x)
     }
 }
 

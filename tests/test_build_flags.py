@@ -86,8 +86,6 @@ def test_spmm_kernels_use_tma_bulk_copies_and_wide_loads(sass):
     assert len(wide) > 40
     for k, ops in wide.items():
         assert any(name.startswith("LDG.E.128") for name in ops), (k, "no 128-bit global loads")
-    # the vector kernel prefetches its diagonal B rows into L2 through the TMA unit
-    assert any(ops.get("UBLKPF") for k, ops in spmm.items() if "spmm_rows_kernel" in k), "no bulk L2 prefetch (UBLKPF) in the vector kernel"
 
 
 def test_instantiation_table_stays_bounded(sass):

