@@ -37,7 +37,8 @@ struct PipelineStreams {
     cudaEvent_t ev[16] = {};
 };
 int pipeline_streams(PipelineStreams **out);
-// a small pinned host buffer owned by the runtime (grown on demand, never shrunk): readbacks without a cudaHostAlloc per call
+// a small pinned, device-mapped host buffer owned by the runtime (grown on demand, never shrunk): readbacks without a cudaHostAlloc
+// per call, and scalars a kernel stores straight into host memory (unified addressing: the host pointer is valid on the device)
 int pinned_scratch(void **p, size_t bytes);
 
 // Per-phase wall-clock timers of the host-to-host calls (BSM_PHASE_TIMERS=1, or bsm_phase_timers_enable):

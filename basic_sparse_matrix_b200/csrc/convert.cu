@@ -505,18 +505,28 @@ int launch_scatter_nonzero64(int dtype, const void *dense, uint64_t rows, uint64
 
 // row_index piece of row block k in the reference layout: out64[i] = entries before the block (tot[k]) + the block-local
 // exclusive scan; tot[k+1] = tot[k] + entries of the block (local_rp[rows])
+// host_tot (mapped pinned host memory) receives tot[k+1] by a plain store over PCIe — NOT by a copy: a cudaMemcpyAsync of these
+// 8 bytes queues on the device->host copy engine behind gigabytes of result blocks (measured: ~30 ms late per block)
 __global__ void row_index_piece_kernel(const uint32_t *__restrict__ local_rp, uint64_t rows, unsigned long long *__restrict__ tot, uint32_t k,
-                                       uint64_t *__restrict__ out64)
+                                       uint64_t *__restrict__ out64, volatile unsigned long long *host_tot)
 {
     const unsigned long long base = tot[k];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += stride) out64[i] = base + local_rp[i];
-    if (blockIdx.x == 0 && threadIdx.x == 0) tot[k + 1] = base + local_rp[rows];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long next = base + local_rp[rows];
+        tot[k + 1] = next;
+        if (host_tot) {
+            host_tot[k + 1] = next;
+            __threadfence_system();
+        }
+    }
 }
 
-int launch_row_index_piece(const uint32_t *local_rp, uint64_t rows, unsigned long long *tot, uint32_t k, uint64_t *out64, cudaStream_t stream)
+int launch_row_index_piece(const uint32_t *local_rp, uint64_t rows, unsigned long long *tot, uint32_t k, uint64_t *out64,
+                           unsigned long long *host_tot, cudaStream_t stream)
 {
-    row_index_piece_kernel<<<grid_for(std::max<uint64_t>(rows, 1), 256), 256, 0, stream>>>(local_rp, rows, tot, k, out64);
+    row_index_piece_kernel<<<grid_for(std::max<uint64_t>(rows, 1), 256), 256, 0, stream>>>(local_rp, rows, tot, k, out64, host_tot);
     BSM_CUDA(cudaGetLastError());
     count_launch();
     return BSM_OK;

@@ -103,7 +103,7 @@ int launch_block_col_range(const uint32_t *row_ptr, const uint32_t *col_idx, uin
 int launch_scatter_nonzero64(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, const uint32_t *row_ptr, void *vals,
                              uint64_t *col_index, cudaStream_t stream);
 int launch_row_index_piece(const uint32_t *local_rp, uint64_t rows, unsigned long long *tot /* [nblocks+1] */, uint32_t k, uint64_t *out64,
-                           cudaStream_t stream);
+                           unsigned long long *host_tot /* mapped pinned mirror of tot, or null */, cudaStream_t stream);
 int launch_fill_u32(uint32_t *dst, uint64_t count, uint32_t value, cudaStream_t stream);
 
 // ---- synthetic generators (gen.cu) -----------------------------------------------------------------

@@ -346,8 +346,7 @@ template <typename T> int host_product(const HostProduct<T> &q)
                 BSM_TRY(launch_count_nonzero(q.dtype, cv.data, rbk, n, ld, counts[o], nullptr, s_mm));
                 BSM_TRY(exclusive_scan_u32(counts[o], counts[o], rbk + 1, s_mm));
                 BSM_TRY(launch_scatter_nonzero64(q.dtype, cv.data, rbk, n, ld, counts[o], vals_st[o], cols_st[o], s_mm));
-                BSM_TRY(launch_row_index_piece(counts[o], rbk, tot, k, rp64[o], s_mm));
-                BSM_CUDA(cudaMemcpyAsync(h_tot + k + 1, tot + k + 1, 8, cudaMemcpyDeviceToHost, s_mm));
+                BSM_TRY(launch_row_index_piece(counts[o], rbk, tot, k, rp64[o], h_tot, s_mm));   // also stores the running total to the host
                 tl.end(s_mm);
             } else {
                 tl.begin(PH_C_TRANSPOSE, s_mm);

@@ -98,7 +98,7 @@ int pinned_scratch(void **p, size_t bytes)
         g_pin = nullptr;
         g_pin_bytes = 0;
         const size_t want = std::max<size_t>(bytes, 64 << 10);
-        BSM_CUDA(cudaHostAlloc(&g_pin, want, cudaHostAllocDefault));
+        BSM_CUDA(cudaHostAlloc(&g_pin, want, cudaHostAllocMapped | cudaHostAllocPortable));   // mapped: kernels can store results into it
         g_pin_bytes = want;
     }
     *p = g_pin;

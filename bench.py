@@ -494,6 +494,34 @@ def pinned(torch, shape, np_dtype):
     return torch.empty(shape, dtype=tdt).pin_memory().numpy().view(np_dtype)
 
 
+def pcie_probe(torch, barrier, min_over_ranks, mb=512, reps=3):
+    """What the platform gives every rank when ALL ranks copy at once: plain pinned-buffer copies (no library code), host->device
+    only, device->host only, and both directions together. The ceiling the e2e numbers are to be read against."""
+    n = mb << 20
+    h_in, h_out = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty(n, dtype=torch.uint8, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    out = {}
+    for name in ("h2d", "d2h", "duplex"):
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if name in ("h2d", "duplex"):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if name in ("d2h", "duplex"):
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+        dt = time.perf_counter() - t0
+        out[name + "_gbs_per_direction_slowest_rank"] = round(min_over_ranks(n * reps / dt / 1e9), 1)
+    out["note"] = f"all ranks at once, {mb} MB pinned buffers, torch copy_ on two streams; per direction, slowest rank"
+    return out
+
+
 def mem_available_gb():
     try:
         for line in open("/proc/meminfo"):
@@ -558,6 +586,12 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return float(t.item())
 
     kind, prm, n, dt = WORKLOADS[args.workload]
@@ -787,6 +821,10 @@ def main():
             return max_over_ranks(te), ph
 
         steps_e = max(1, args.e2e_steps)
+        try:
+            pcie = pcie_probe(torch, barrier, min_over_ranks)
+        except Exception as ex:
+            pcie = {"error": str(ex)[:200]}
         # (1) dense result
         out_cols = [torch.empty(ai["rows"], dtype=torch_dt).pin_memory().numpy() for _ in range(n)]
         hC = Dense.from_columns_nocopy(out_cols)
@@ -820,7 +858,7 @@ def main():
                    "result": "Csr (zero-dropped, usize indices) — the reference's return type", "result_nnz_rank0": nnz_out,
                    "parity": {"rows_checked": int(len(chk_ids)) * world, "bitwise": all_true(bitwise_equal(got_rows, want_rows)),
                               "checker": "CPU oracle; rows of the returned Csr densified (dropped zeros = 0)"},
-                   "phases_ms_rank0": ph, "numa": numa,
+                   "phases_ms_rank0": ph, "numa": numa, "pcie_probe": pcie,
                    "path": "Csr.mul_dense_csr_into -> bsm_mul_dense_host_into_*: the literal Csr::mul_dense (sparse.rs:426-446): host Csr + host Dense "
                            "columns in, zero-dropped host Csr out; pipeline = A up | B up in row chunks + transpose | per row block SpMM + count/scan/scatter | "
                            "values + usize columns + row_index down; pinned host buffers"}

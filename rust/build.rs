@@ -6,8 +6,9 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
     let nvcc = format!("{cuda}/bin/nvcc");
-    let sources = ["bsm_api.cu", "spmm_rows.cu", "spmm_rows_f64.cu", "spmm_rows_f32.cu", "spmm_merge.cu", "spmm_rowblock.cu", "convert.cu", "gen.cu",
-                   "bsm_nccl.cu"];
+    // the same list as SRCS in basic_sparse_matrix_b200/csrc/Makefile (tests/test_rust_ffi.py compares the two)
+    let sources = ["runtime.cu", "handles.cu", "planner.cu", "dispatch.cu", "pipeline.cu", "solve.cu", "gen_api.cu", "spmm_rows.cu",
+                   "spmm_rows_f64.cu", "spmm_rows_f32.cu", "spmm_merge.cu", "spmm_rowblock.cu", "convert.cu", "gen.cu", "bsm_nccl.cu"];
     let mut objects = Vec::new();
     for src in sources {
         let obj = out.join(format!("{src}.o"));
@@ -31,7 +32,7 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=nccl");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for hdr in ["bsm_common.cuh", "kernels.h", "spmm_stream.cuh", "spmm_rows_kernel.cuh", "spmm_rows_inst.cuh", "bsm.h"] {
+    for hdr in ["bsm_common.cuh", "bsm_internal.h", "line_length.h", "kernels.h", "spmm_stream.cuh", "spmm_rows_kernel.cuh", "spmm_rows_inst.cuh", "bsm.h"] {
         println!("cargo:rerun-if-changed=csrc/{hdr}");
     }
 }

@@ -27,3 +27,13 @@ def test_every_header_function_is_bound_and_every_used_binding_exists():
     assert used <= bound, used - bound
     consts = set(re.findall(r"ffi::(BSM_\w+)", mod))
     assert consts <= set(re.findall(r"pub const (BSM_\w+)", ffi)), consts
+
+
+def test_build_rs_compiles_the_same_sources_as_the_makefile():
+    mk = open(os.path.join(ROOT, "basic_sparse_matrix_b200", "csrc", "Makefile")).read()
+    srcs = re.search(r"^SRCS := (.*)$", mk, flags=re.M).group(1).split()
+    rs = open(os.path.join(ROOT, "rust", "build.rs")).read()
+    listed = re.findall(r'"(\w+\.cu)"', rs[rs.index("let sources"):rs.index("let mut objects")])
+    assert sorted(srcs) == sorted(listed), (set(srcs) ^ set(listed))
+    for f in srcs:
+        assert os.path.exists(os.path.join(ROOT, "basic_sparse_matrix_b200", "csrc", f)), f
