@@ -215,7 +215,7 @@ int plan_vector_pass(const MatrixFacts &m, const DeviceFacts &dev, const bsm_tun
         p.R = R;
         p.stages = user_stages ? (uint32_t)std::min(tn.stages, 8) : (grouped && grouped_by_default && sh.G >= 8 ? 2u : 3u);
         auto smem_now = [&]() {
-            p.cap = (uint32_t)pad4((uint64_t)p.R * m.max_row_nnz + 3) + 2 * window + 4;
+            p.cap = (uint32_t)pad4((uint64_t)p.R * m.max_row_nnz + 3) + (uint32_t)pad4(2 * window) + 4;   // a multiple of 4: the stage arrays stay 16-byte aligned
             return row_kernel_smem_bytes(m.dtype, p, nw);
         };
         size_t smem = smem_now();
