@@ -382,6 +382,50 @@ def run_extra(torch, gpu, name, steps, warmup, peak, tuning=None, label=None):
     return out
 
 
+def run_solve(torch, gpu, n_rows=1 << 20, hb=32, nrhs=32):
+    """BASELINE configs[4], the part after the factorisation: L y = b and L* x = y (lib.rs:28-65) for 32 right-hand sides on
+    the device, against the CPU port of the same two loops (oracle/ref_solve_band.c, 1 thread), on a synthetic band factor
+    (values do not matter for the timing; the factorisation itself stays on the CPU and is not timed). X is compared bit for bit."""
+    from basic_sparse_matrix_b200 import Csr, gen
+    from oracle import ref_solve
+    f32 = np.float32
+    rng = np.random.default_rng(11)
+    l_band = np.zeros((n_rows, hb + 1), f32)                       # band storage of a lower-triangular factor
+    l_band[:, :hb] = rng.uniform(-0.02, 0.02, (n_rows, hb)).astype(f32)
+    l_band[:, hb] = rng.uniform(1.0, 2.0, n_rows).astype(f32)
+    for i in range(min(hb, n_rows)):                                # columns < 0 do not exist
+        l_band[i, :hb - i] = 0
+    b_cols = gen.dense_rows(n_rows, nrhs, 6, gen.MODE_REAL, 0.5, f32).T.copy()
+    L = gpu.DeviceCsr.from_host(Csr.from_raw_parts((n_rows, n_rows), *ref_solve.band_to_csr_lower(l_band)))
+    Ls = gpu.DeviceCsr.from_host(Csr.from_raw_parts((n_rows, n_rows), *ref_solve.band_to_csr_upper(l_band)))
+    B = gpu.DeviceDense.generate(n_rows, nrhs, seed=6, mode=gen.MODE_REAL, offset=0.5, dtype=f32)
+    Y, X = gpu.DeviceDense.alloc(n_rows, nrhs, f32), gpu.DeviceDense.alloc(n_rows, nrhs, f32)
+    L.forward_substitution(B, out=Y)                                # warm-up
+    Ls.backward_substitution(Y, out=X)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    L.forward_substitution(B, out=Y)
+    e[1].record()
+    Ls.backward_substitution(Y, out=X)
+    e[2].record()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    y_ref = np.stack([ref_solve.forward(l_band, b_cols[c]) for c in range(nrhs)])
+    t1 = time.perf_counter()
+    x_ref = np.stack([ref_solve.backward(l_band, y_ref[c]) for c in range(nrhs)])
+    t2 = time.perf_counter()
+    same = bitwise_equal(X.to_rowmajor().T, x_ref)
+    nnz = int(L.info()["nnz"])
+    for h in (L, Ls, B, Y, X):
+        h.close()
+    return {"workload": f"band_{n_rows}_hb{hb}_solve_n{nrhs}_f32", "what": "forward + backward substitution (lib.rs:28-65), factor given", "rows": n_rows,
+            "factor_nnz": nnz, "forward_ms": round(e[0].elapsed_time(e[1]), 2), "backward_ms": round(e[1].elapsed_time(e[2]), 2),
+            "cpu_port_forward_ms": round((t1 - t0) * 1e3, 1), "cpu_port_backward_ms": round((t2 - t1) * 1e3, 1), "cpu_cores": 1,
+            "x_equals_cpu_port_bitwise": same,
+            "note": "rows are sequential by construction (latency-bound); one lane per right-hand side, one warp per 32 of them"}
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU baseline = the reference's CPU path (C restatement, 1 thread) on a bounded sample
 # ---------------------------------------------------------------------------------------------
@@ -894,6 +938,10 @@ def main():
             extras.append(run_extra(torch, gpu, "band_1m_hb32_n32_f32", 10, 3, peak, fused, "band_1m_hb32_n32_f32 [BSM_TUNE_FUSED opt-in]"))
         except Exception as ex:
             extras.append({"workload": "band_1m_hb32_n32_f32 [BSM_TUNE_FUSED opt-in]", "error": str(ex)[:200]})
+        try:
+            extras.append(run_solve(torch, gpu))
+        except Exception as ex:
+            extras.append({"workload": "band solve", "error": str(ex)[:200]})
         try:
             extras.append(run_config1(torch, gpu, peak))
         except Exception as ex:

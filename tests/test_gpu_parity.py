@@ -242,6 +242,32 @@ def test_rowblock_bitwise(gpu, dtype):
         assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, random_dense(np.random.default_rng(1), k, 64, dtype)), "rowblock col_tile")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_rowblock_fused_is_within_tolerance(gpu, dtype):
+    """BSM_TUNE_FUSED (opt-in, never a default): the row-block kernel with one FMA per product instead of the reference's
+    separately rounded multiply and add. Agreement is then the stated tolerance (1e-12 f64 / 1e-5 f32 of sum|a*b|), not bitwise;
+    on exactly representable data it is still bit-exact. Shapes without a fused variant are refused, not silently unfused."""
+    rng = np.random.default_rng(808)
+    m = k = 2003
+    v, ci, ri = _runs_csr(rng, m, k, dtype, 65, band=True)
+    fused = _lib.TUNE_A_EVICT_FIRST | _lib.TUNE_C_STREAMING | _lib.TUNE_FUSED
+    per16 = 16 // np.dtype(dtype).itemsize
+    for lanes in (8, 32):
+        n = per16 * lanes
+        b = random_dense(rng, k, n, dtype)
+        for rb in (4, 8):
+            got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "rowblock", flags=fused, rows_per_slice=rb)
+            assert info["algo"] == _lib.ALGO_ROWBLOCK
+            assert_tolerance(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), ref_numpy.abs_product_sum(v, ci, ri, b), TOL[dtype], f"fused n={n} rb={rb}")
+        ve = (np.round(v * 8) / 8).astype(dtype)
+        be = random_dense(rng, k, n, dtype, exact=True)
+        got, _ = gpu_product(gpu, (m, k), ve, ci, ri, be, "rowblock", flags=fused)
+        assert_bitwise(got, ref_numpy.mul_dense_rowmajor(ve, ci, ri, be), f"fused, exact data n={n}")
+    with pytest.raises(_lib.BsmError) as e:       # 3 columns: no 128-bit lanes, no fused variant
+        gpu_product(gpu, (m, k), v, ci, ri, random_dense(rng, k, 3, dtype), "rowblock", flags=fused)
+    assert e.value.status == _lib.BSM_ERR_NOT_SUPPORTED
+
+
 def test_rowblock_refuses_rows_that_are_not_runs_and_auto_picks_it_for_bands(gpu):
     rng = np.random.default_rng(607)
     v, ci, ri = random_csr(rng, 300, 300, np.float64, mean_len=6)
