@@ -123,6 +123,7 @@ def _declare(L):
     sig("bsm_csr_from_device", i32, i32, u64, u64, u64, vp, vp, vp, i32, PV)
     sig("bsm_csr_free", i32, vp)
     sig("bsm_csr_info", i32, vp, C.POINTER(i32), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64))
+    sig("bsm_csr_stats", i32, vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64))
     sig("bsm_csr_device_ptrs", i32, vp, PV, PV, PV)
     sig("bsm_dense_alloc", i32, i32, u64, u64, PV)
     sig("bsm_dense_borrow", i32, i32, u64, u64, vp, u64, PV)

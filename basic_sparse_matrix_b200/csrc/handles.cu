@@ -377,6 +377,16 @@ int bsm_csr_info(const bsm_csr *a, int *dtype, uint64_t *rows, uint64_t *cols, u
     return BSM_OK;
 }
 
+int bsm_csr_stats(const bsm_csr *a, uint64_t *max_row_nnz, uint64_t *col_min, uint64_t *col_max, uint64_t *line_length)
+{
+    if (!a) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_stats: null handle");
+    if (max_row_nnz) *max_row_nnz = a->max_row_nnz;
+    if (col_min) *col_min = a->col_min;
+    if (col_max) *col_max = a->col_max;
+    if (line_length) *line_length = a->row_stride;
+    return BSM_OK;
+}
+
 int bsm_csr_device_ptrs(const bsm_csr *a, const void **d_vals, const uint32_t **d_col_idx, const uint32_t **d_row_ptr)
 {
     if (!a) return fail(BSM_ERR_INVALID_ARGUMENT, "csr_device_ptrs: null handle");

@@ -247,6 +247,12 @@ class DeviceCsr(_Handle):
         check(lib().bsm_csr_info(self.handle, C.byref(dt), C.byref(r), C.byref(c), C.byref(nnz), C.byref(mx)))
         return {"dtype": _lib.np_dtype(dt.value), "rows": r.value, "cols": c.value, "nnz": nnz.value, "max_row_nnz": mx.value}
 
+    def stats(self) -> dict:
+        """What the upload measured over all rows: longest row, column range, majority stencil line length (0 = none)."""
+        mx, lo, hi, ll = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(lib().bsm_csr_stats(self.handle, C.byref(mx), C.byref(lo), C.byref(hi), C.byref(ll)))
+        return {"max_row_nnz": mx.value, "col_min": lo.value, "col_max": hi.value, "line_length": ll.value}
+
     def get_dims(self) -> MatDim:
         i = self.info()
         return MatDim(i["rows"], i["cols"])

@@ -160,6 +160,10 @@ int bsm_csr_from_device(int dtype, uint64_t rows, uint64_t cols, uint64_t nnz, c
 int bsm_csr_free(bsm_csr *a);
 int bsm_csr_info(const bsm_csr *a, int *dtype, uint64_t *rows, uint64_t *cols, uint64_t *nnz,
                  uint64_t *max_row_nnz);
+/* The per-matrix statistics the dispatch heuristics use, computed once at upload by one kernel over ALL rows: smallest / largest
+ * stored column, and the stencil line length the majority of rows suggests (0 = not stencil-like) — the number of consecutive
+ * rows a warp of the vector kernel owns so that the warps of a CTA sweep adjacent grid lines. Any pointer may be NULL. */
+int bsm_csr_stats(const bsm_csr *a, uint64_t *max_row_nnz, uint64_t *col_min, uint64_t *col_max, uint64_t *line_length);
 /* device pointers of the three arrays (for zero-copy views, e.g. torch.from_dlpack-free use) */
 int bsm_csr_device_ptrs(const bsm_csr *a, const void **d_vals, const uint32_t **d_col_idx,
                         const uint32_t **d_row_ptr);

@@ -211,6 +211,38 @@ def test_vector_slow_path_rows_longer_than_a_stage(gpu):
     assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), "slow path")
 
 
+def test_line_length_is_a_majority_vote_over_all_rows(gpu):
+    """The stencil line length comes from ALL rows (one statistics kernel, warp-aggregated votes), not from three sampled rows:
+    a Laplacian whose rows at 1/4, 1/2 and 3/4 (round 1's sample points) are anything but stencil rows is still recognised;
+    matrices without a majority are not; the column range and the longest row come from the same kernel."""
+    g = 48
+    v, ci, ri, dims = gen.laplacian(g, g, g)
+    n = g ** 3
+    with gpu.DeviceCsr.from_host(host_csr(dims, v, ci, ri)) as a:
+        assert a.stats() == {"max_row_nnz": 7, "col_min": 0, "col_max": n - 1, "line_length": g}
+    ci2 = ci.copy()
+    for q in (1, 2, 3):                              # scramble the three rows round 1 sampled
+        r = n // 4 * q
+        s, e = int(ri[r]), int(ri[r + 1])
+        ci2[s:e] = np.sort(np.random.default_rng(q).choice(n, e - s, replace=False)).astype(np.uint64)
+    with gpu.DeviceCsr.from_host(host_csr(dims, v, ci2, ri)) as a:
+        assert a.stats()["line_length"] == g
+    # permuted copies of two stencils (line lengths 48 and 36 in equal parts): no majority -> no line length
+    v2, c2, r2, d2 = gen.laplacian(36, 64, 48)      # same number of rows: 36*64*48 == 48^3
+    assert d2[0] == n
+    vv = np.concatenate([v[: int(ri[n // 2])], v2[int(r2[n // 2]):]])
+    cc = np.concatenate([ci[: int(ri[n // 2])], c2[int(r2[n // 2]):]])
+    rr = np.concatenate([ri[: n // 2], r2[n // 2:] - r2[n // 2] + ri[n // 2]])
+    with gpu.DeviceCsr.from_host(host_csr(dims, vv, cc, rr)) as a:
+        assert a.stats()["line_length"] in (0, g, 36)   # exactly half each: whichever has >= half of the rows, or none
+    rng = np.random.default_rng(5)
+    vr, cr, rrr = random_csr(rng, 9000, 7000, np.float64, mean_len=6)
+    with gpu.DeviceCsr.from_host(host_csr((9000, 7000), vr, cr, rrr)) as a:
+        st = a.stats()
+        assert st["line_length"] == 0 and st["col_max"] == int(cr.max()) and st["col_min"] == int(cr.min())
+        assert st["max_row_nnz"] == int(np.diff(rrr.astype(np.int64)).max())
+
+
 # ---- row-block kernel (band-like matrices) -----------------------------------------------------------------
 def _runs_csr(rng, m, k, dtype, max_len, empty_frac=0.1, band=True):
     """Every row stores one run of consecutive columns (a band when band=True, else runs anywhere)."""
