@@ -119,6 +119,8 @@ uint32_t column_tile(const bsm_tuning &tn, uint32_t n_total, int vmax, uint32_t 
 // ---- dispatch.cu -------------------------------------------------------------------------------------------
 // C = A * B on `stream` (the C-ABI entry points pass the library stream; the pipelines pass their own)
 int spmm_dispatch(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const bsm_tuning *tuning, cudaStream_t stream);
+// does every row of the matrix store a run of consecutive columns? (the row-block probe: one kernel per handle, cached)
+int csr_rows_are_runs(const bsm_csr *a, cudaStream_t stream, bool *runs);
 // which kernel family bsm_spmm would run for `requested` (bsm_algo; AUTO = the heuristics) on n_cols columns
 int resolve_algo(const bsm_csr *a, uint64_t n_cols, int requested, int *algo, cudaStream_t stream);
 

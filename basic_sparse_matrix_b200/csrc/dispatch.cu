@@ -336,6 +336,14 @@ static int choose_algo(const bsm_csr *a_const, uint64_t n_cols, int requested, i
     return BSM_OK;
 }
 
+int csr_rows_are_runs(const bsm_csr *a_const, cudaStream_t stream, bool *runs)
+{
+    bsm_csr *a = const_cast<bsm_csr *>(a_const);   // the probe result is cached in the handle
+    BSM_TRY(ensure_rowblock_probe(a, stream));
+    *runs = a->rowblock_state == 1;
+    return BSM_OK;
+}
+
 int resolve_algo(const bsm_csr *a, uint64_t n_cols, int requested, int *algo, cudaStream_t stream)
 {
     return choose_algo(a, n_cols, requested, algo, stream);
