@@ -100,6 +100,53 @@ template <typename F> static float time_ms(F f, int reps = 5)
     return best;
 }
 
+// The vector kernel's traversal without its arithmetic: persistent CTAs of `warps` warps; CTA b owns super-batches b, b+grid, ... of
+// warps*P consecutive 1 KB rows; warp w copies rows [w*P, (w+1)*P) of it one row (32 lanes x 2 x 16 bytes) at a time with `u` rows
+// of loads in flight; `extra` further rows are read per row at the stencil offsets (+-1 line = P rows, +-1 plane) and discarded,
+// to reproduce the gather traffic (L1 / L2 hits) next to the streams. What copy bandwidth does the TRAVERSAL allow?
+template <int U>
+__global__ void __launch_bounds__(256, 3) pattern_copy_kernel(const double2 *__restrict__ a, double2 *__restrict__ b, uint32_t rows, uint32_t P,
+                                                              uint32_t plane, int gathers, double *sink)
+{
+    const uint32_t W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t S = W * P, num_super = (rows + S - 1) / S;
+    double acc = 0.0;
+    for (uint32_t sb = blockIdx.x; sb < num_super; sb += gridDim.x) {
+        const uint32_t r0 = sb * S + warp * P, r1 = min(rows, r0 + P);
+        for (uint32_t r = r0; r < r1; r += U) {
+            double2 v[U][2];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + u < r1) {
+                    v[u][0] = __ldg(a + (size_t)(r + u) * 64 + lane);
+                    v[u][1] = __ldg(a + (size_t)(r + u) * 64 + 32 + lane);
+                }
+            if (gathers) {   // the six neighbour rows of a 7-point stencil row (mostly L1 / L2 hits)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (r + u < r1) {
+                        const long long offs[6] = {-(long long)plane, -(long long)P, -1, 1, (long long)P, (long long)plane};
+#pragma unroll
+                        for (int g = 0; g < 6; ++g) {
+                            const long long j = (long long)(r + u) + offs[g];
+                            if (g < gathers && j >= 0 && j < (long long)rows) {
+                                const double2 x = __ldg(a + (size_t)j * 64 + lane), y = __ldg(a + (size_t)j * 64 + 32 + lane);
+                                acc += x.x + y.y;
+                            }
+                        }
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + u < r1) {
+                    __stcs(b + (size_t)(r + u) * 64 + lane, v[u][0]);
+                    __stcs(b + (size_t)(r + u) * 64 + 32 + lane, v[u][1]);
+                }
+        }
+    }
+    if (acc == 123.456) *sink = acc;
+}
+
 int main()
 {
     cudaDeviceProp prop;
@@ -125,6 +172,18 @@ int main()
     printf("DRAM copy   %8.1f GB/s (read+write bytes)\n", 2.0 * big / ms / 1e6);
     ms = time_ms([&] { CK(cudaMemcpyAsync(b, a, big, cudaMemcpyDeviceToDevice)); });
     printf("cudaMemcpy  %8.1f GB/s (read+write bytes)\n", 2.0 * big / ms / 1e6);
+
+    {   // 4 GB = 4 Mi rows of 1 KB (64 planes of a 256^3 grid's B): the vector kernel's traversal as a plain copy
+        const uint32_t rows = (uint32_t)(big / 1024);
+        for (int gathers : {0, 2, 6})
+            for (uint32_t P : {16u, 64u, 256u, 1024u}) {
+                ms = time_ms([&] { pattern_copy_kernel<4><<<sms * 3, 256>>>(a, b, rows, P, 65536u, gathers, sink); });
+                printf("pattern copy, %d neighbour rows read, 3 CTAs x 8 warps, %4u rows per warp, 4 rows in flight: %8.1f GB/s (read+write bytes of the copy)\n",
+                       gathers, P, 2.0 * big / ms / 1e6);
+            }
+        ms = time_ms([&] { pattern_copy_kernel<8><<<sms * 2, 256>>>(a, b, rows, 256u, 65536u, 0, sink); });
+        printf("pattern copy, 0 neighbour rows, 2 CTAs x 8 warps,  256 rows per warp, 8 rows in flight: %8.1f GB/s\n", 2.0 * big / ms / 1e6);
+    }
 
     for (size_t mb : {8, 16, 32, 48, 64, 96, 128, 192}) {
         const size_t bytes = mb << 20;
