@@ -230,11 +230,20 @@ __global__ void __launch_bounds__(256) merge_fixup_long_kernel(const MergeParams
 // ------------------------------------------------------------------------------------------
 constexpr int merge_default_u(int NT) { return NT >= 4 ? 4 : (NT == 2 ? 4 : 8); }
 
+// The unpredicated (FULLN) form is built for the shapes that carry the measured workloads — 128-bit lanes, a full warp with one
+// or two register tiles, and the grouped shapes; every other shape runs the predicated form, whose extra cost disappears behind
+// the gathers (the kernel is bound by the L1 data pipe and L2, §3.2 of DESIGN.md). Halves the size of this object.
 template <typename T, int V, int G, int NT> static const void *merge_kernel_ptr(bool fulln)
 {
     constexpr int U = merge_default_u(NT);
-    return fulln ? reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT, true, U>)
-                 : reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT, false, U>);
+    constexpr bool kBuildFull = V * sizeof(T) == 16 && ((G == 32 && NT <= 2) || (G < 32 && NT == 2));
+    if constexpr (kBuildFull) {
+        if (fulln) return reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT, true, U>);
+    }
+    if constexpr (G < 32 && NT > 1)
+        return nullptr;   // the grouped shapes exist for full-width rows only
+    else
+        return reinterpret_cast<const void *>(&spmm_merge_kernel<T, V, G, NT, false, U>);
 }
 template <typename T, int V> static const void *merge_kernel_select_gnt(int G, int NT, bool fulln)
 {

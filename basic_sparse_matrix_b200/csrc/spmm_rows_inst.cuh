@@ -42,16 +42,18 @@ template <typename T, int V, int NT> static const void *rk_wide(bool fulln, int 
     // scatter variant: bound by the P2P stores over NVLink, not by the SM — one (predicated, staged) kernel per shape
     if (multi) return flavour < 0 ? nullptr : rk<T, V, 32, NT, false, U1, 512, 1, true, true, true>();
     if (flavour < 0) return rk<T, V, 32, NT, false, U1, 512, 1, false>();   // unstaged: one (predicated) variant serves full-width shapes too
-    if (fulln) {
-        switch (flavour) {
-            case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();
-            case 6: return rk<T, V, 32, NT, true, U1, 768, 1, true, false>();  // ONE CTA of 24 warps per SM (24 adjacent lines share L1)
-            case 7:   // one tile per lane: window of 10 gathers — as deep as 85 registers allow without spilling
-                if constexpr (NT == 1) return rk<T, V, 32, NT, true, 10, 768, 1, true, false>();
-                else return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // (deeper windows measured slower with several tiles)
+    if constexpr (V * sizeof(T) == 16) {   // the register-budget flavours are built for 128-bit lanes (one-element lanes: the default)
+        if (fulln) {
+            switch (flavour) {
+                case 4: return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();
+                case 6: return rk<T, V, 32, NT, true, U1, 768, 1, true, false>();  // ONE CTA of 24 warps per SM (24 adjacent lines share L1)
+                case 7:   // one tile per lane: window of 10 gathers — as deep as 85 registers allow without spilling
+                    if constexpr (NT == 1) return rk<T, V, 32, NT, true, 10, 768, 1, true, false>();
+                    else return rk<T, V, 32, NT, true, U1, 256, 3, true, false>();   // (deeper windows measured slower with several tiles)
+            }
         }
-        return rk<T, V, 32, NT, true, U1, 512, 1>();
     }
+    if (fulln) return rk<T, V, 32, NT, true, U1, 512, 1>();
     return rk<T, V, 32, NT, false, U1, 512, 1>();
 }
 
