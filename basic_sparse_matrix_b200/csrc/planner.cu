@@ -2,6 +2,7 @@
 // (bsm_plan_vector answers it as a dry run, which is how tests/test_launch_plan.py pins every heuristic on the CPU),
 // and the nnz-balanced row partition of the multi-GPU path.
 #include <algorithm>
+#include <cmath>
 #include <string>
 
 #include "bsm_internal.h"
@@ -166,6 +167,11 @@ int plan_vector_pass(const MatrixFacts &m, const DeviceFacts &dev, const bsm_tun
         const bool wide_full = sh.G == 32 && n == (uint32_t)(sh.V * sh.G * sh.NT);
         const uint32_t rpp = 32u / (uint32_t)sh.G;   // rows side by side in one warp
         const uint32_t rq = std::max(4u, rpp);       // slice granularity (rpp is a power of two)
+        // 64-byte output rows (four 128-bit lanes, one tile) on short regular rows: every lane group walks ONE flat entry stream over
+        // its run of rows instead of row by row, so the eight gather windows of a warp never drain at a row end (flavour 8;
+        // 3-D Laplacian x8 f64 1.26 -> 0.96 ms, profiles/r2_sweep_flat_narrow_*.jsonl; two-lane shapes and long rows do not gain)
+        const bool flat_narrow = !multi && !scatter && !grouped && sh.G == 4 && sh.NT == 1 && (size_t)sh.V * s == 16 &&
+                                 (tn.reg_flavour == 9 || (tn.reg_flavour <= 0 && !user_nw && mean <= 16.0 && (double)m.max_row_nnz <= 4.0 * mean + 8.0));
 
         // rows per TMA slice: ~128 entries per bulk copy (~224 with one register tile per lane, r1_sweepi_*, and for
         // 8 lanes x 2 tiles); narrow shapes want several row passes per slice to amortise the slice bookkeeping
@@ -176,6 +182,8 @@ int plan_vector_pass(const MatrixFacts &m, const DeviceFacts &dev, const bsm_tun
             const double target = ((sh.G == 32 && sh.NT == 1) || (grouped && grouped_by_default && sh.NT == 2)) ? 224.0 : 128.0;
             R = (uint32_t)std::min<double>(256.0, std::max(1.0, target / std::max(1.0, mean)));
             if (sh.G < 32) R = std::max(R, 4u * rpp);
+            // a flat stream wants ~56 entries per lane group and slice (seven window turns after one turn of prologue)
+            if (flat_narrow) R = rpp * (uint32_t)std::min(16.0, std::max(4.0, std::ceil(56.0 / std::max(1.0, mean))));
         }
         R = std::max(rq, R / rq * rq);
         // a stencil-like matrix: the slice must divide the line length, or the rows per warp (a multiple of the
@@ -191,6 +199,7 @@ int plan_vector_pass(const MatrixFacts &m, const DeviceFacts &dev, const bsm_tun
         }
 
         int flavour = pick_row_flavour(tn, sh, wide_full, grouped, grouped_by_default, multi);
+        if (flat_narrow) flavour = 8;
         // warps per CTA: what the flavour was compiled for; fewer on small matrices, so that no SM idles behind a
         // handful of fat super-batches
         const bool big_cta = (wide_full && (flavour == 5 || flavour == 6 || flavour == 7)) || (grouped && flavour == 6);

@@ -38,7 +38,7 @@ int launch_spmm_rows(int dtype, Shape sh, const RowParams &p, int flavour, bool 
     const void *k = row_kernel_select(dtype, sh, p.n, flavour, multi);
     if (!k) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rows: no kernel for this lane shape");
     if (p.stages < 1 || p.stages > (uint32_t)kMaxStages) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_rows: stages out of range");
-    const bool flat = sh.G == 32 || sh.NT > 1;   // flat-stream shapes accept any P >= R, the row-by-row ones need whole slices
+    const bool flat = sh.G == 32 || sh.NT > 1 || flavour == 8;   // flat-stream shapes accept any P >= R, the row-by-row ones need whole slices
     if (p.R == 0 || p.R % 4 || p.P < p.R || (!flat && p.P % p.R))
         return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_rows: inconsistent slice geometry");
     BSM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -7,10 +7,10 @@ namespace bsm {
 
 constexpr int row_default_u(int NT) { return NT >= 4 ? 2 : (NT == 2 ? 4 : 8); }
 
-template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true, bool MULTI = false>
+template <typename T, int V, int G, int NT, bool FULLN, int U, int MAXT, int MINB, bool STAGED = true, bool VECA = true, bool MULTI = false, bool FLAT = false>
 static const void *rk()
 {
-    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI>);
+    return reinterpret_cast<const void *>(&spmm_rows_kernel<T, V, G, NT, FULLN, U, MAXT, MINB, STAGED, VECA, MULTI, FLAT>);
 }
 
 // Register-budget flavours (`flavour` argument of the selectors = bsm_tuning.reg_flavour - 1):
@@ -19,6 +19,8 @@ static const void *rk()
 //   6: one CTA of up to 768 threads per SM (<= 85 registers), scalar reads                       — default for grouped lanes
 //   7: flavour 6 with a window of 10 gathers when a lane holds one register tile (else flavour 4) — default for one tile per lane
 //   (narrow one-tile shapes: 0, and for a row per lane 4 = scalar reads)
+//   8: narrow one-tile shapes of 4 x 128-bit lanes as flat entry streams per lane group (flavour 0 otherwise) — default for 64-byte
+//      output rows on short regular rows
 //  -1: flavour 0 without TMA staging of col_idx / values (slices longer than a stage can hold)
 // Flavours 1, 2, 3, 5 of round 1 (window twice as deep; LDS.128 reads at 3 CTAs / at 768 threads; 4 CTAs at 64 registers) lost
 // every sweep they were in (profiles/r1_sweep{i,s}_*.jsonl) and are no longer built: 1 runs as 0, 2 and 3 as 4, 5 as 6.
@@ -63,6 +65,9 @@ template <typename T, int V, int G> static const void *rk_narrow(bool fulln, int
     if (flavour < 0) return rk<T, V, G, 1, false, 8, 512, 1, false>();   // unstaged: one (predicated) variant
     if constexpr (G == 1) {   // a row per lane (SpMV): scalar reads of the staged col_idx / values
         if (flavour == 4) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, false>() : rk<T, V, G, 1, false, 8, 512, 1, true, false>();
+    }
+    if constexpr (G == 4 && V * sizeof(T) == 16) {   // flat entry streams (8 rows side by side never drain their windows at a row end)
+        if (flavour == 8) return fulln ? rk<T, V, G, 1, true, 8, 512, 1, true, true, false, true>() : rk<T, V, G, 1, false, 8, 512, 1, true, true, false, true>();
     }
     return fulln ? rk<T, V, G, 1, true, 8, 512, 1>() : rk<T, V, G, 1, false, 8, 512, 1>();
 }
@@ -117,6 +122,6 @@ template <typename T, int V> static const void *row_kernel_select_v(Shape sh, bo
 }
 
 // largest CTA (threads) a flavour was compiled for
-inline int row_flavour_max_threads(int flavour) { return flavour >= 2 ? 256 : 512; }
+inline int row_flavour_max_threads(int flavour) { return flavour >= 2 && flavour != 8 ? 256 : 512; }
 
 }  // namespace bsm

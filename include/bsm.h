@@ -97,7 +97,9 @@ typedef struct bsm_tuning {
     int32_t reg_flavour;     /* vector kernel: register-budget variant. 0 = heuristic; 1 = CTAs of <= 512
                                 threads, 1 per SM; 5 = CTAs of <= 256 threads, 3 per SM, scalar reads of the staged
                                 col_idx / values; 7 = one CTA of <= 768 threads per SM, scalar reads; 8 = 7 with a
-                                window of 10 gathers (one register tile per lane). 2, 3, 4, 6 = variants the round-1
+                                window of 10 gathers (one register tile per lane); 9 = four 128-bit lanes per row walking
+                                flat entry streams (the default for 64-byte output rows on short regular rows; other
+                                shapes run it as 8). 2, 3, 4, 6 = variants the round-1
                                 sweeps rejected (deeper window, LDS.128 reads): no longer built, they run as 1, 5, 5, 7
                                 (see csrc/spmm_rows_inst.cuh)                                        */
     int32_t lanes_per_row;   /* vector kernel: lanes that share one output row (power of two <= 32). 0 = heuristic.

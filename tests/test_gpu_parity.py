@@ -185,6 +185,37 @@ def test_vector_grouped_lanes_bitwise(gpu, dtype):
                     assert_bitwise(got, want, f"grouped m={m} n={n} G={g} NT={nt} {tune}")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_vector_flat_narrow_streams_bitwise(gpu, dtype):
+    """64-byte output rows (four 128-bit lanes per row) as flat entry streams per lane group (reg_flavour 9, the default on short
+    regular rows): rows of very different lengths side by side, empty rows and groups, slices shorter than the group count,
+    rows per warp that are no multiple of the slice, a partial last column group (n = 6 of 8 f64 / 12 of 16 f32)."""
+    rng = np.random.default_rng(123)
+    per16 = 16 // np.dtype(dtype).itemsize
+    for m, k in ((3001, 3001), (5, 40), (1, 9), (67, 500), (4099, 2000)):
+        mats = [_near_diagonal_csr(rng, m, k, dtype), random_csr(rng, m, k, dtype, mean_len=6, giant_row=min(3, m - 1), giant_len=150)]
+        for mi, (v, ci, ri) in enumerate(mats):
+            for n in (4 * per16, 3 * per16):
+                b = random_dense(rng, k, n, dtype)
+                want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+                for tune in (dict(), dict(reg_flavour=9), dict(reg_flavour=9, rows_per_slice=8, rows_per_warp=24),
+                             dict(reg_flavour=9, rows_per_slice=16, rows_per_warp=50), dict(reg_flavour=9, rows_per_slice=128, stages=2, warps_per_cta=3)):
+                    got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "vector", **tune)
+                    if tune and mi == 0:   # (a giant row that cannot be staged falls back to the unstaged row-by-row kernel — by design)
+                        assert (info["lanes_per_row"], info["reg_tiles"], info["reg_flavour"]) == (4, 1, 9), info
+                    assert_bitwise(got, want, f"flat narrow m={m} n={n} {tune} launched {info}")
+    # the default picks it for a stencil matrix
+    a = gpu.DeviceCsr.laplacian(24, 24, 24, dtype=dtype)
+    v, ci, ri, _ = gen.laplacian(24, 24, 24, dtype=dtype)
+    n = 4 * per16
+    b = gpu.DeviceDense.generate(24 ** 3, n, seed=5, mode=gen.MODE_REAL, dtype=dtype)
+    c = a.mul_dense(b, algo="vector")
+    assert gpu.last_launch_info()["reg_flavour"] == 9, gpu.last_launch_info()
+    assert_bitwise(c.to_rowmajor(), ref_numpy.mul_dense_rowmajor(v, ci, ri, gen.dense_rows(24 ** 3, n, 5, gen.MODE_REAL, dtype=dtype)), "flat narrow default")
+    for h in (a, b, c):
+        h.close()
+
+
 @pytest.mark.parametrize("g", [50, 37])
 def test_vector_stencil_line_length_not_a_multiple_of_four(gpu, g):
     """3-D Laplacian on a g^3 grid with g = 50 / 37: the rows per warp follow the line length (50, 37), so warps start

@@ -51,6 +51,20 @@ def test_narrow_rows_are_grouped_on_short_regular_rows(dtype, n, lanes, tiles):
     assert p["rows_per_warp"] == 256
 
 
+@pytest.mark.parametrize("dtype,n", [(F64, 8), (F32, 16)])
+def test_64_byte_rows_walk_flat_streams_on_short_regular_rows(dtype, n):
+    # four 128-bit lanes per row, 8 rows side by side, each lane group one flat entry stream over 8 rows of a 64-row slice
+    p = plan(dtype, L3D["rows"], L3D["nnz"], L3D["max_row"], 256, n)
+    assert (p["lanes_per_row"], p["reg_tiles"], p["reg_flavour"]) == (4, 1, 9)
+    assert (p["rows_per_slice"], p["rows_per_warp"], p["stages"], p["block"]) == (64, 256, 2 if dtype == F64 else 3, 512)
+    # long or uneven rows stay row by row; so do two-lane shapes
+    assert plan(dtype, 1 << 20, 68_156_384, 65, 0, n)["reg_flavour"] == 1
+    assert plan(dtype, L3D["rows"], L3D["nnz"], 60, 0, n)["reg_flavour"] == 1
+    assert plan(dtype, L3D["rows"], L3D["nnz"], L3D["max_row"], 256, n // 2)["reg_flavour"] == 1
+    # explicit request
+    assert plan(dtype, 1 << 20, 68_156_384, 65, 0, n, reg_flavour=9)["reg_flavour"] == 9
+
+
 def test_long_rows_stay_row_by_row_on_narrow_shapes():
     # band, half-bandwidth 32, x 32 f32 (when the row-block kernel is not used): 8 lanes, one tile, row by row
     p = plan(F32, 1 << 20, 68_156_384, 65, 0, 32)
