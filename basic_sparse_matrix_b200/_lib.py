@@ -141,6 +141,7 @@ def _declare(L):
     sig("bsm_dense_to_csr", i32, vp, PV)
     sig("bsm_dense_residual_norm", i32, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double))
     sig("bsm_forward_substitution", i32, vp, vp, vp)
+    sig("bsm_csr_band_structure", i32, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32))
     sig("bsm_backward_substitution", i32, vp, vp, vp)
     sig("bsm_host_free", None, vp)
     sig("bsm_partition_rows", i32, vp, u64, i32, vp)

@@ -69,6 +69,11 @@ struct bsm_csr {
     // columns, 2 = not; rowblock_union = B rows the row-block kernel would load (vs nnz for the vector kernel)
     int rowblock_state = 0;
     uint64_t rowblock_union = 0;
+    // band probe (solve.cu), run on first use by a substitution: 0 = not probed, 1 = probed. band_lower / band_upper: the matrix is a
+    // proper lower / upper band factor of half-bandwidth band_hb (every row stores exactly the band's columns, diagonal last / first)
+    int band_state = 0;
+    bool band_lower = false, band_upper = false;
+    uint32_t band_hb = 0;
     // merge-path partition cache (depends only on A and the item count)
     int part_items = 0;
     uint32_t part_chunks = 0;

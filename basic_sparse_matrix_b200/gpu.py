@@ -247,6 +247,12 @@ class DeviceCsr(_Handle):
         check(lib().bsm_csr_info(self.handle, C.byref(dt), C.byref(r), C.byref(c), C.byref(nnz), C.byref(mx)))
         return {"dtype": _lib.np_dtype(dt.value), "rows": r.value, "cols": c.value, "nnz": nnz.value, "max_row_nnz": mx.value}
 
+    def band_structure(self) -> dict:
+        """Half-bandwidth when the matrix is a proper lower / upper band factor (what the substitutions specialise on), else -1."""
+        lo, up = C.c_int32(-1), C.c_int32(-1)
+        check(lib().bsm_csr_band_structure(self.handle, C.byref(lo), C.byref(up)))
+        return {"lower_hb": lo.value, "upper_hb": up.value}
+
     def stats(self) -> dict:
         """What the upload measured over all rows: longest row, column range, majority stencil line length (0 = none)."""
         mx, lo, hi, ll = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)

@@ -242,6 +242,13 @@ int bsm_dense_residual_norm(const bsm_dense *ax, const bsm_dense *b, double *res
  * (Csr::cholesky_decomp, sparse.rs:682-714, and transpose) is out of scope and stays with the caller. */
 int bsm_forward_substitution(const bsm_csr *l, const bsm_dense *b, bsm_dense *y);
 int bsm_backward_substitution(const bsm_csr *l_star, const bsm_dense *y, bsm_dense *x);
+/* Which substitution kernel a factor gets (probed on the device once per handle, cached). *lower_hb / *upper_hb = the
+ * half-bandwidth when the matrix is a PROPER lower / upper band factor — row r stores exactly the columns
+ * max(0, r-hb) .. r (diagonal last) / r .. min(n-1, r+hb) (diagonal first), what cholesky_decomp and transpose() produce for a
+ * band matrix (sparse.rs:682-714, 296-318) — else -1. Proper band factors of half-bandwidth 8, 16 or 32 with at least 4 hb rows
+ * run a specialised kernel (one solver warp, no hand-overs between warps; same arithmetic, same bits); everything else the general
+ * one. Either pointer may be NULL. */
+int bsm_csr_band_structure(const bsm_csr *a, int32_t *lower_hb, int32_t *upper_hb);
 
 /* Host-to-host convenience = the literal reference call: uploads A and B, multiplies, compacts
  * and returns the zero-dropped result Csr in reference layout. The result arrays are allocated

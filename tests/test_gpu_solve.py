@@ -138,3 +138,97 @@ def test_band_solve_matches_the_reference_solve_bitwise(gpu, n_rows):
             gpu.DeviceDense.generate(n_rows, nrhs, seed=6, mode=gen.MODE_REAL, offset=0.5, dtype=f32) as b:
         with l.forward_substitution(b) as y, ls.backward_substitution(y) as x:
             assert_bitwise(x.to_rowmajor().T, x_ref, "device substitutions vs reference solve")
+
+
+# ---- proper band factors: the specialised kernels (one solver warp, staging warps) ------------------------------------------
+def _band_factor(rng, n, hb, dtype, upper=False, ragged_row=None):
+    """Raw Csr parts of a proper lower (diagonal last) / upper (diagonal first) band factor of half-bandwidth hb."""
+    vals, cols, ri = [], [], [0]
+    for r in range(n):
+        off_cols = list(range(r + 1, min(n, r + hb + 1))) if upper else list(range(max(0, r - hb), r))
+        if ragged_row is not None and r == ragged_row and off_cols:
+            off_cols = off_cols[1:] if not upper else off_cols[:-1]      # one entry short: no longer a proper band
+        offv = rng.uniform(-0.05, 0.05, len(off_cols)).tolist()
+        diag = float(rng.uniform(1.0, 2.0))
+        cols += ([r] + off_cols) if upper else (off_cols + [r])
+        vals += ([diag] + offv) if upper else (offv + [diag])
+        ri.append(len(cols))
+    return np.array(vals, dtype), np.array(cols, np.uint64), np.array(ri, np.uint64)
+
+
+def _substitute_np(v, ci, ri, b_cols, upper):
+    """lib.rs:35-42 / 56-60 with the right-hand sides vectorised: one numpy operation per stored entry, all columns at once (every
+    operation separately rounded in the array dtype, in stored order — the same arithmetic as ref_solve.forward_csr / backward_csr,
+    which the small cases below are also checked against)."""
+    n = b_cols.shape[1]
+    x = np.zeros_like(b_cols)
+    ci = ci.astype(np.int64)
+    ri = ri.astype(np.int64)
+    for r in (range(n - 1, -1, -1) if upper else range(n)):
+        lx = np.zeros(b_cols.shape[0], b_cols.dtype)
+        s, e = ri[r], ri[r + 1]
+        for k in (range(s + 1, e) if upper else range(s, e)):
+            if upper or ci[k] != r:
+                lx = lx + v[k] * x[:, ci[k]]
+        x[:, r] = (b_cols[:, r] - lx) / (v[s] if upper else v[e - 1])
+    return x
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("hb", [8, 16, 32])
+def test_band_kernels_bitwise(gpu, dtype, hb, monkeypatch):
+    """Proper band factors take the specialised kernels: checked against the restatement of lib.rs:28-65 AND against the general
+    kernel (BSM_SOLVE_GENERAL=1), for row counts around the batch / group sizes and ragged numbers of right-hand sides."""
+    from oracle import ref_solve
+    rng = np.random.default_rng(1000 + hb)
+    for n, nrhs in ((4 * hb, 1), (4 * hb + 3, 33), (4 * hb + 16, 5), (1000 + hb, 32), (2049, 45)):
+        b_cols = rng.uniform(0.5, 1.5, (nrhs, n)).astype(dtype)
+        with gpu.DeviceDense.from_rowmajor(np.ascontiguousarray(b_cols.T)) as b_dev:
+            for upper in (False, True):
+                v, ci, ri = _band_factor(rng, n, hb, dtype, upper=upper)
+                want = _substitute_np(v, ci, ri, b_cols, upper)
+                if n <= 4 * hb + 3:
+                    small = (ref_solve.backward_csr if upper else ref_solve.forward_csr)(v, ci, ri, b_cols)
+                    assert_bitwise(want, small, "vectorised restatement vs statement-by-statement restatement")
+                with gpu.DeviceCsr.from_host(Csr.from_raw_parts((n, n), v, ci, ri)) as l:
+                    bs = l.band_structure()
+                    assert bs == ({"lower_hb": -1, "upper_hb": hb} if upper else {"lower_hb": hb, "upper_hb": -1}), bs
+                    sub = l.backward_substitution if upper else l.forward_substitution
+                    with sub(b_dev) as x:
+                        got = x.to_rowmajor().T
+                    monkeypatch.setenv("BSM_SOLVE_GENERAL", "1")
+                    with sub(b_dev) as x:
+                        general = x.to_rowmajor().T
+                    monkeypatch.delenv("BSM_SOLVE_GENERAL")
+                assert_bitwise(got, want, f"band kernel hb={hb} n={n} nrhs={nrhs} upper={upper}")
+                assert_bitwise(general, want, f"general kernel hb={hb} n={n} nrhs={nrhs} upper={upper}")
+
+
+def test_band_probe_rejects_everything_else(gpu):
+    rng = np.random.default_rng(3)
+    n, hb = 300, 16
+    cases = {
+        "ragged row": _band_factor(rng, n, hb, f32, ragged_row=150),
+        "half-bandwidth the kernels are not built for": _band_factor(rng, n, 12, f32),
+        "adversarial": _random_factor(rng, n, f32),
+    }
+    b_cols = rng.uniform(0.5, 1.5, (3, n)).astype(f32)
+    from oracle import ref_solve
+    with gpu.DeviceDense.from_rowmajor(np.ascontiguousarray(b_cols.T)) as b_dev:
+        for name, (v, ci, ri) in cases.items():
+            with gpu.DeviceCsr.from_host(Csr.from_raw_parts((n, n), v, ci, ri)) as l:
+                bs = l.band_structure()
+                assert bs["upper_hb"] == -1 and bs["lower_hb"] == (12 if "built for" in name else -1), (name, bs)
+                with l.forward_substitution(b_dev) as y:
+                    assert_bitwise(y.to_rowmajor().T, ref_solve.forward_csr(v, ci, ri, b_cols), name)
+    # special values travel exactly like in the reference: an infinite right-hand side entry turns the rows below into NaN / inf
+    v, ci, ri = _band_factor(rng, 200, 8, f32)
+    b_cols = rng.uniform(0.5, 1.5, (2, 200)).astype(f32)
+    b_cols[0, 37] = np.inf
+    b_cols[1, 120] = np.nan
+    with gpu.DeviceDense.from_rowmajor(np.ascontiguousarray(b_cols.T)) as b_dev, \
+            gpu.DeviceCsr.from_host(Csr.from_raw_parts((200, 200), v, ci, ri)) as l, l.forward_substitution(b_dev) as y:
+        with np.errstate(all="ignore"):
+            want = _substitute_np(v, ci, ri, b_cols, False)
+        got = y.to_rowmajor().T
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
