@@ -232,3 +232,56 @@ def test_band_probe_rejects_everything_else(gpu):
             want = _substitute_np(v, ci, ri, b_cols, False)
         got = y.to_rowmajor().T
         assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(want)], want[~np.isnan(want)])
+
+
+@pytest.mark.parametrize("upper", [False, True])
+def test_band_kernels_zero_and_special_right_hand_sides(gpu, upper):
+    """Zero numerators (a zero column, -0.0 entries) stay on the band kernels' division shortcut and keep the sign of their zeros;
+    infinities, NaN, subnormals and solutions that decay towards them make the library fall back to the general kernel —
+    bit-identical either way."""
+    rng = np.random.default_rng(17)
+    n, hb = 700, 32
+    v, ci, ri = _band_factor(rng, n, hb, f32, upper=upper)
+    b_cols = rng.uniform(0.5, 1.5, (6, n)).astype(f32)
+    b_cols[0, :] = 0.0                         # a zero column: every numerator is +-0
+    b_cols[1, ::2] = -0.0
+    b_cols[2, 5] = -0.0
+    with np.errstate(all="ignore"):
+        want = _substitute_np(v, ci, ri, b_cols, upper)
+    with gpu.DeviceDense.from_rowmajor(np.ascontiguousarray(b_cols.T)) as b_dev, \
+            gpu.DeviceCsr.from_host(Csr.from_raw_parts((n, n), v, ci, ri)) as l:
+        sub = l.backward_substitution if upper else l.forward_substitution
+        with gpu.DeviceDense.from_rowmajor(np.ascontiguousarray(rng.uniform(0.5, 1.5, (n, 6)).astype(f32))) as b_plain:
+            sub(b_plain).close()                                  # (the probes of a new handle run here)
+            c0 = gpu.kernel_launch_count()
+            sub(b_plain).close()
+            plain_launches = gpu.kernel_launch_count() - c0       # what one substitution on the band kernel launches
+        c0 = gpu.kernel_launch_count()
+        with sub(b_dev) as x:
+            launches = gpu.kernel_launch_count() - c0
+            assert_bitwise(x.to_rowmajor().T, want, "zero numerators")
+        assert launches == plain_launches, "zero numerators must not leave the band kernel"
+    # (a unit vector: the solution decays below 2^-90 a few dozen rows after the one, then through the subnormals to zero)
+    for special in (float(np.inf), float(np.nan), f32(1e-42), f32(3e38), "unit vector"):
+        b2 = b_cols.copy()
+        if special == "unit vector":
+            b2[3, :] = 0.0
+            b2[3, 350] = 1.0
+        else:
+            b2[3, 350] = special
+        with np.errstate(all="ignore"):
+            want = _substitute_np(v, ci, ri, b2, upper)
+        with gpu.DeviceDense.from_rowmajor(np.ascontiguousarray(b2.T)) as b_dev, \
+                gpu.DeviceCsr.from_host(Csr.from_raw_parts((n, n), v, ci, ri)) as l:
+            sub = l.backward_substitution if upper else l.forward_substitution
+            sub(b_dev).close()
+            c0 = gpu.kernel_launch_count()
+            with sub(b_dev) as x:
+                # (the subnormal right-hand side entry disappears in b - l_x: that numerator is an ordinary number)
+                extra = gpu.kernel_launch_count() - c0 - plain_launches
+                if isinstance(special, float):                     # inf, nan
+                    assert extra == 1, f"{special}: expected the general kernel after the band kernel"
+                assert extra in (0, 1)
+                got = x.to_rowmajor().T
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan) and np.array_equal(got[~nan].view(np.uint32), want[~nan].view(np.uint32)), special
