@@ -11,6 +11,6 @@ st = torch.cuda.Stream(); gpu.set_stream(st.cuda_stream); torch.cuda.set_stream(
 r = bench.run_solve(torch, gpu, n_rows=1 << 18)
 print(json.dumps({k: r[k] for k in ("forward_ms", "backward_ms", "x_equals_cpu_port_bitwise")}))
 PY
-for v in lib lib_NOSHFL lib_NOSTG; do
+for v in lib lib_NOPRED lib_NORANGE; do
   BSM_B200_LIB=$PWD/basic_sparse_matrix_b200/$v/libbsm_b200.so timeout 300 python gpurun_out/solve_full.py 2>&1 | tail -1 | sed "s/^/$v: /"
 done
