@@ -33,7 +33,7 @@ void dev_free(void *p, bool pooled);
 
 // Streams and events of the host-to-host pipelines, created once per process (not per call).
 struct PipelineStreams {
-    cudaStream_t in = nullptr, mm = nullptr, out = nullptr;
+    cudaStream_t in = nullptr, mm = nullptr, out = nullptr, meta = nullptr;   // meta: the small pieces of a result block (row masks, row_index)
     cudaEvent_t ev[16] = {};
 };
 int pipeline_streams(PipelineStreams **out);

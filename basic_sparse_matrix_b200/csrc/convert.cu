@@ -352,19 +352,31 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t count, cudaSt
 template <typename T> __device__ __forceinline__ bool keep(T x) { return x != T(0); }
 
 // one warp per row
+// masks (optional): bit c % 64 of masks[r * words + c / 64] = entry (r, c) is kept — the result's column indices in 1 bit instead
+// of 8 bytes each (what the pipelined host call sends over PCIe instead of the usize columns)
 template <typename T>
 __global__ void count_nonzero_kernel(const T *__restrict__ d, uint64_t rows, uint64_t cols, uint64_t ld,
-                                     uint32_t *__restrict__ counts, unsigned long long *total)
+                                     uint32_t *__restrict__ counts, unsigned long long *total, uint64_t *__restrict__ masks)
 {
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
+    const uint64_t words = (cols + 63) / 64;
     unsigned long long local = 0;
     for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
         uint32_t n = 0;
+        uint64_t w = 0;
         for (uint64_t c0 = 0; c0 < cols; c0 += 32) {
             const uint64_t c = c0 + lane;
             const bool k = c < cols && keep(d[r * ld + c]);
-            n += __popc(__ballot_sync(0xFFFFFFFFu, k));
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, k);
+            n += __popc(m);
+            if (masks) {
+                w |= (uint64_t)m << (c0 & 32u);
+                if (lane == 0 && ((c0 & 32u) || c0 + 32 >= cols)) {
+                    masks[r * words + c0 / 64] = w;
+                    w = 0;
+                }
+            }
         }
         if (lane == 0) {
             counts[r] = n;
@@ -400,14 +412,14 @@ __global__ void scatter_nonzero_kernel(const T *__restrict__ d, uint64_t rows, u
 }
 
 int launch_count_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t *counts,
-                         unsigned long long *total, cudaStream_t stream)
+                         unsigned long long *total, cudaStream_t stream, uint64_t *masks)
 {
     if (rows == 0) return BSM_OK;
     const int grid = grid_for(rows * 32, 256);
     if (dtype == BSM_F64)
-        count_nonzero_kernel<double><<<grid, 256, 0, stream>>>((const double *)dense, rows, cols, ld, counts, total);
+        count_nonzero_kernel<double><<<grid, 256, 0, stream>>>((const double *)dense, rows, cols, ld, counts, total, masks);
     else
-        count_nonzero_kernel<float><<<grid, 256, 0, stream>>>((const float *)dense, rows, cols, ld, counts, total);
+        count_nonzero_kernel<float><<<grid, 256, 0, stream>>>((const float *)dense, rows, cols, ld, counts, total, masks);
     BSM_CUDA(cudaGetLastError());
     count_launch();
     return BSM_OK;
@@ -482,7 +494,7 @@ __global__ void scatter_nonzero64_kernel(const T *__restrict__ d, uint64_t rows,
             if (k) {
                 const uint32_t o = pos + __popc(m & ((1u << lane) - 1u));   // ascending column = insertion order
                 vals[o] = x;
-                col_index[o] = c;
+                if (col_index) col_index[o] = c;   // (null: the columns travel as row masks, see count_nonzero_kernel)
             }
             pos += __popc(m);
         }

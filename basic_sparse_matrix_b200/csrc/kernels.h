@@ -95,7 +95,7 @@ int launch_transpose_rm2cm(int dtype, const void *rowmajor, void *colmajor, uint
 int launch_widen_u32(const uint32_t *src, uint64_t *dst, uint64_t count, cudaStream_t stream);
 int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t count, cudaStream_t stream);  // out may alias in
 int launch_count_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t *counts,
-                         unsigned long long *total, cudaStream_t stream);
+                         unsigned long long *total, cudaStream_t stream, uint64_t *masks = nullptr /* [rows][ceil(cols/64)] keep-bits, optional */);
 int launch_scatter_nonzero(int dtype, const void *dense, uint64_t rows, uint64_t cols, uint64_t ld,
                            const uint32_t *row_ptr, void *vals, uint32_t *col_idx, cudaStream_t stream);
 int launch_block_col_range(const uint32_t *row_ptr, const uint32_t *col_idx, uint64_t rows, uint64_t block_rows, uint32_t nblocks,

@@ -3,10 +3,17 @@
 // Csr::mul_vector (468-482) and the residual norms of BASELINE config 5.
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include "bsm_internal.h"
 
@@ -100,6 +107,127 @@ struct DevTimeline {
     }
 };
 
+// The column indices of the result travel as ROW MASKS, not as usize values. The result of Csr x Dense is dense unless a sum
+// happens to be exactly zero, so the returned Csr spends 8 bytes per entry on columns that say "0 .. n-1" in nearly every row —
+// half of the device -> host traffic of the literal call, which is what bounds it. The device sends one keep-bit per output
+// (count_nonzero_kernel writes them while it counts: n/8 bytes per row instead of 8 n), and a few host threads expand the masks of a
+// row block into the caller's col_index while the values of the next blocks travel: a full row is one copy of the pattern
+// 0 .. n-1, any other row is walked bit by bit. Same arrays, same contents as the reference's insert / finalise produce.
+// BSM_PIPE_EXPAND_THREADS = number of threads (default 8, at most half of the hardware threads; 0 = the device writes usize
+// columns and they are copied, as before). Measured on the headline product (34.5 GB of result): 717-772 ms -> 530-600 ms; the
+// call is then bound by the host -> device copy of B, which the expansion's memory traffic slows from 350 to 500 ms.
+class ColumnExpand {
+    struct Job {
+        cudaEvent_t landed;            // the block's masks and row_index piece are in host memory
+        const uint64_t *masks;         // [rows][words]
+        const uint64_t *row_index;     // absolute offsets of the rows into col_index
+        uint64_t *col_index;
+        uint64_t rows, n, words;
+    };
+    std::vector<std::thread> threads_;
+    std::deque<Job> jobs_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool closing_ = false;
+    int want_;
+    int device_ = 0;
+    std::vector<uint64_t> pattern_;   // 0 .. n-1
+    bool nt_ = true;                  // non-temporal stores for full rows: no read-for-ownership of 17 GB nobody reads soon (BSM_PIPE_EXPAND_NT=0: plain)
+
+    void fill_row(uint64_t *dst, uint64_t n) const
+    {
+#if defined(__x86_64__)
+        if (nt_) {
+            const uint64_t *pat = pattern_.data();
+            uint64_t i = 0;
+            if ((uintptr_t)dst & 15) {
+                _mm_stream_si64(reinterpret_cast<long long *>(dst), 0);
+                i = 1;
+            }
+            for (; i + 1 < n; i += 2) _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i *>(pat + i)));
+            if (i < n) _mm_stream_si64(reinterpret_cast<long long *>(dst + i), (long long)i);
+            return;
+        }
+#endif
+        memcpy(dst, pattern_.data(), n * 8);
+    }
+
+    void work()
+    {
+        cudaSetDevice(device_);
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return closing_ || !jobs_.empty(); });
+                if (jobs_.empty()) return;
+                j = jobs_.front();
+                jobs_.pop_front();
+            }
+            cudaEventSynchronize(j.landed);
+            const uint64_t full_tail = (j.n & 63) ? ((1ull << (j.n & 63)) - 1ull) : ~0ull;
+            for (uint64_t r = 0; r < j.rows; ++r) {
+                const uint64_t *m = j.masks + r * j.words;
+                uint64_t *dst = j.col_index + j.row_index[r];
+                bool full = m[j.words - 1] == full_tail;
+                for (uint64_t w = 0; full && w + 1 < j.words; ++w) full = m[w] == ~0ull;
+                if (full) {
+                    fill_row(dst, j.n);
+                    continue;
+                }
+                for (uint64_t w = 0; w < j.words; ++w)
+                    for (uint64_t bits = m[w]; bits; bits &= bits - 1) *dst++ = w * 64 + (uint64_t)__builtin_ctzll(bits);
+            }
+        }
+    }
+
+public:
+    ColumnExpand()
+    {
+        const char *e = getenv("BSM_PIPE_EXPAND_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        want_ = (e && *e) ? atoi(e) : std::min(8, std::max(1, hw / 2));
+        if (want_ < 0) want_ = 0;
+        const char *nt = getenv("BSM_PIPE_EXPAND_NT");   // 0 = plain stores (same-box A/B: 634-659 ms against 596-604 ms with non-temporal ones)
+        nt_ = !(nt && *nt == '0');
+        cudaGetDevice(&device_);
+    }
+    bool enabled() const { return want_ > 0; }
+    // rows of one block; returns at once, the rows are split over the threads
+    void expand(cudaEvent_t landed, const uint64_t *masks, const uint64_t *row_index, uint64_t *col_index, uint64_t rows, uint64_t n)
+    {
+        if (rows == 0 || n == 0) return;
+        const uint64_t words = (n + 63) / 64;
+        if (pattern_.size() != n) {
+            pattern_.resize(n);
+            for (uint64_t i = 0; i < n; ++i) pattern_[i] = i;
+        }
+        const uint64_t parts = std::min<uint64_t>((uint64_t)want_ * 2, std::max<uint64_t>(1, rows * n / (1u << 20)));
+        const uint64_t step = (rows + parts - 1) / parts;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (uint64_t r = 0; r < rows; r += step)
+                jobs_.push_back(Job{landed, masks + r * words, row_index + r, col_index, std::min(step, rows - r), n, words});
+        }
+        if (threads_.empty())
+            for (int t = 0; t < want_; ++t) threads_.emplace_back([this] { work(); });
+        cv_.notify_all();
+    }
+    // everything issued so far is done when this returns
+    void finish()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            closing_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread &t : threads_) t.join();
+        threads_.clear();
+        closing_ = false;
+    }
+    ~ColumnExpand() { finish(); }
+};
+
 template <typename T> struct HostProduct {
     int dtype;
     uint64_t rows, cols, nnz;
@@ -166,6 +294,8 @@ template <typename T> int host_product(const HostProduct<T> &q)
     PipelineStreams *ps = nullptr;
     cudaStream_t lib = rt().stream;
     DevTimeline tl;
+    ColumnExpand expand;
+    std::vector<cudaEvent_t> ev_landed;   // per row block: its masks and row_index piece have reached the host
     // geometry
     const uint64_t ld = default_ld(n, q.dtype);
     uint64_t rb = std::max<uint64_t>(4, pipe_rows(rows, ld * s, s, env_bytes("BSM_PIPE_BLOCK_BYTES")) / 4 * 4);       // rows per block (multiple of 4: the row_ptr
@@ -182,7 +312,9 @@ template <typename T> int host_product(const HostProduct<T> &q)
     const uint64_t win_rows = win_hi - win_lo;
 
     T *bwin = nullptr, *cdev = nullptr, *stage_in[2] = {}, *stage_out[2] = {}, *vals_st[2] = {};
-    uint64_t *cols_st[2] = {}, *rp64[2] = {};
+    uint64_t *cols_st[2] = {}, *rp64[2] = {}, *masks_st[2] = {}, *h_masks = nullptr;
+    const uint64_t mwords = (n + 63) / 64;   // keep-bit words per result row
+    const bool by_masks = want_csr && expand.enabled();   // columns travel as row masks, expanded by host threads
     uint32_t *counts[2] = {}, *blk_range = nullptr;
     unsigned long long *tot = nullptr, *h_tot = nullptr;
     uint32_t *h_range = nullptr;
@@ -190,7 +322,7 @@ template <typename T> int host_product(const HostProduct<T> &q)
 
     int st = [&]() -> int {
         BSM_TRY(pipeline_streams(&ps));
-        cudaStream_t s_in = ps->in, s_mm = ps->mm, s_out = ps->out;
+        cudaStream_t s_in = ps->in, s_mm = ps->mm, s_out = ps->out, s_meta = ps->meta;
         cudaEvent_t ev_ready = ps->ev[0], *ev_in = &ps->ev[1], *ev_in_free = &ps->ev[3], *ev_c = &ps->ev[5], *ev_out_free = &ps->ev[7];
         // which kernel family: decided once, on the whole matrix
         int algo = BSM_ALGO_VECTOR;
@@ -198,9 +330,15 @@ template <typename T> int host_product(const HostProduct<T> &q)
         const bool per_block = algo != BSM_ALGO_MERGE && nblocks > 1;   // the merge-path partition is per matrix: one SpMM over all rows
         // pinned scratch for the per-block entry counts and the per-block column ranges
         void *pin = nullptr;
-        BSM_TRY(pinned_scratch(&pin, ((size_t)nblocks + 1) * 8 + (size_t)nblocks * 8));
+        const size_t small = round_up(((size_t)nblocks + 1) * 8 + (size_t)nblocks * 8, 256);
+        BSM_TRY(pinned_scratch(&pin, small + (by_masks ? (size_t)rows * mwords * 8 : 0)));
         h_tot = (unsigned long long *)pin;
         h_range = (uint32_t *)(h_tot + nblocks + 1);
+        h_masks = (uint64_t *)((char *)pin + small);
+        if (by_masks) {
+            ev_landed.resize(nblocks, nullptr);
+            for (uint32_t k = 0; k < nblocks; ++k) BSM_CUDA(cudaEventCreateWithFlags(&ev_landed[k], cudaEventDisableTiming));
+        }
         // device buffers (stream-ordered pool on the library stream; the pipeline streams wait for ev_ready)
         BSM_TRY(tmp_alloc((void **)&bwin, std::max<uint64_t>(win_rows, 1) * ld * s + 16));
         BSM_TRY(tmp_alloc((void **)&cdev, rows * ld * s + 16));
@@ -209,7 +347,10 @@ template <typename T> int host_product(const HostProduct<T> &q)
             if (want_csr) {
                 BSM_TRY(tmp_alloc((void **)&counts[i], (pad4(rb + 1) + 4) * 4));
                 BSM_TRY(tmp_alloc((void **)&vals_st[i], rb * n * s));
-                BSM_TRY(tmp_alloc((void **)&cols_st[i], rb * n * 8));
+                if (by_masks)
+                    BSM_TRY(tmp_alloc((void **)&masks_st[i], rb * mwords * 8));
+                else
+                    BSM_TRY(tmp_alloc((void **)&cols_st[i], rb * n * 8));
                 BSM_TRY(tmp_alloc((void **)&rp64[i], rb * 8));
             } else {
                 BSM_TRY(tmp_alloc((void **)&stage_out[i], rb * n * s));
@@ -237,6 +378,7 @@ template <typename T> int host_product(const HostProduct<T> &q)
         BSM_CUDA(cudaStreamWaitEvent(s_in, ev_ready, 0));
         BSM_CUDA(cudaStreamWaitEvent(s_mm, ev_ready, 0));
         BSM_CUDA(cudaStreamWaitEvent(s_out, ev_ready, 0));
+        BSM_CUDA(cudaStreamWaitEvent(s_meta, ev_ready, 0));
         streams_touched = true;
 
         bsm_dense bd, cd;   // B as the kernels see it: row j at bwin + (j - win_lo) * ld
@@ -286,11 +428,18 @@ template <typename T> int host_product(const HostProduct<T> &q)
                     return fail(BSM_ERR_INVALID_ARGUMENT, "mul_dense: the result arrays are too small (capacity " + std::to_string(q.capacity) +
                                                               " entries, need at least " + std::to_string(base + nk) + ")");
                 tl.begin(PH_D2H, s_out);
-                if (nk) {
-                    BSM_CUDA(cudaMemcpyAsync(q.out_v + base, vals_st[o], nk * s, cudaMemcpyDeviceToHost, s_out));
-                    BSM_CUDA(cudaMemcpyAsync(q.out_col_index + base, cols_st[o], nk * 8, cudaMemcpyDeviceToHost, s_out));
+                if (by_masks) {   // (masks and row_index piece are on their way already, see the block loop)
+                    if (nk) {
+                        BSM_CUDA(cudaMemcpyAsync(q.out_v + base, vals_st[o], nk * s, cudaMemcpyDeviceToHost, s_out));
+                        expand.expand(ev_landed[k], h_masks + r0 * mwords, q.out_row_index + r0, q.out_col_index, rbk, n);
+                    }
+                } else {
+                    if (nk) {
+                        BSM_CUDA(cudaMemcpyAsync(q.out_v + base, vals_st[o], nk * s, cudaMemcpyDeviceToHost, s_out));
+                        BSM_CUDA(cudaMemcpyAsync(q.out_col_index + base, cols_st[o], nk * 8, cudaMemcpyDeviceToHost, s_out));
+                    }
+                    BSM_CUDA(cudaMemcpyAsync(q.out_row_index + r0, rp64[o], rbk * 8, cudaMemcpyDeviceToHost, s_out));
                 }
-                BSM_CUDA(cudaMemcpyAsync(q.out_row_index + r0, rp64[o], rbk * 8, cudaMemcpyDeviceToHost, s_out));
                 tl.end(s_out);
             } else {
                 BSM_CUDA(cudaStreamWaitEvent(s_out, ev_c[o], 0));
@@ -316,6 +465,7 @@ template <typename T> int host_product(const HostProduct<T> &q)
             const uint64_t need_chunks = std::min(chunk_end, (need_hi + cb - 1) / cb);
             while (next_chunk < need_chunks) BSM_TRY(enqueue_chunk(next_chunk++));
             if (k >= 2) BSM_CUDA(cudaStreamWaitEvent(s_mm, ev_out_free[o], 0));
+            if (k >= 2 && by_masks) BSM_CUDA(cudaStreamWaitEvent(s_mm, ev_landed[k - 2], 0));   // masks_st / rp64 of block k-2 have left
             bsm_dense cv = cd;
             cv.data = (char *)cdev + r0 * ld * s;
             cv.rows = rbk;
@@ -343,7 +493,7 @@ template <typename T> int host_product(const HostProduct<T> &q)
                 // result construction of the block: insert's zero-drop (sparse.rs:229) + finalise's row_index (206-219)
                 tl.begin(PH_COMPACT, s_mm);
                 BSM_CUDA(cudaMemsetAsync(counts[o], 0, (pad4(rb + 1) + 4) * 4, s_mm));
-                BSM_TRY(launch_count_nonzero(q.dtype, cv.data, rbk, n, ld, counts[o], nullptr, s_mm));
+                BSM_TRY(launch_count_nonzero(q.dtype, cv.data, rbk, n, ld, counts[o], nullptr, s_mm, by_masks ? masks_st[o] : nullptr));
                 BSM_TRY(exclusive_scan_u32(counts[o], counts[o], rbk + 1, s_mm));
                 BSM_TRY(launch_scatter_nonzero64(q.dtype, cv.data, rbk, n, ld, counts[o], vals_st[o], cols_st[o], s_mm));
                 BSM_TRY(launch_row_index_piece(counts[o], rbk, tot, k, rp64[o], h_tot, s_mm));   // also stores the running total to the host
@@ -354,12 +504,19 @@ template <typename T> int host_product(const HostProduct<T> &q)
                 tl.end(s_mm);
             }
             BSM_CUDA(cudaEventRecord(ev_c[o], s_mm));
+            if (by_masks) {   // the small pieces of the block leave at once, on their own stream: the host threads can start on its columns
+                BSM_CUDA(cudaStreamWaitEvent(s_meta, ev_c[o], 0));
+                BSM_CUDA(cudaMemcpyAsync(h_masks + r0 * mwords, masks_st[o], rbk * mwords * 8, cudaMemcpyDeviceToHost, s_meta));
+                BSM_CUDA(cudaMemcpyAsync(q.out_row_index + r0, rp64[o], rbk * 8, cudaMemcpyDeviceToHost, s_meta));
+                BSM_CUDA(cudaEventRecord(ev_landed[k], s_meta));
+            }
             if (k >= 1) BSM_TRY(drain(k - 1));   // one block behind the compute
         }
         BSM_TRY(drain(nblocks - 1));
         {
             PhaseScope w(PH_WAIT);
             BSM_CUDA(cudaStreamSynchronize(s_out));
+            BSM_CUDA(cudaStreamSynchronize(s_meta));
             BSM_CUDA(cudaStreamSynchronize(s_mm));
             BSM_CUDA(cudaStreamSynchronize(s_in));
         }
@@ -367,8 +524,15 @@ template <typename T> int host_product(const HostProduct<T> &q)
             q.out_row_index[rows] = h_tot[nblocks];   // finalise(): the tail of row_index is nnz
             *q.out_nnz = h_tot[nblocks];
         }
+        {
+            PhaseScope w(PH_WAIT);
+            expand.finish();
+        }
         return BSM_OK;
     }();
+    expand.finish();   // (error paths: nothing may still be writing into the caller's arrays)
+    for (cudaEvent_t e : ev_landed)
+        if (e) cudaEventDestroy(e);
     if (st != BSM_OK && streams_touched) cudaDeviceSynchronize();   // nothing may still be using the buffers freed below
     tl.finish();
     for (int i = 0; i < 2; ++i) {
@@ -376,6 +540,7 @@ template <typename T> int host_product(const HostProduct<T> &q)
         tmp_free(stage_out[i]);
         tmp_free(vals_st[i]);
         tmp_free(cols_st[i]);
+        tmp_free(masks_st[i]);
         tmp_free(rp64[i]);
         tmp_free(counts[i]);
     }

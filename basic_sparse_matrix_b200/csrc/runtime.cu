@@ -74,6 +74,7 @@ int pipeline_streams(PipelineStreams **out)
             cudaStreamDestroy(g_pipe.in);
             cudaStreamDestroy(g_pipe.mm);
             cudaStreamDestroy(g_pipe.out);
+            cudaStreamDestroy(g_pipe.meta);
             for (cudaEvent_t &e : g_pipe.ev)
                 if (e) cudaEventDestroy(e);
             g_pipe = PipelineStreams();
@@ -82,6 +83,7 @@ int pipeline_streams(PipelineStreams **out)
         BSM_CUDA(cudaStreamCreateWithFlags(&g_pipe.in, cudaStreamNonBlocking));
         BSM_CUDA(cudaStreamCreateWithFlags(&g_pipe.mm, cudaStreamNonBlocking));
         BSM_CUDA(cudaStreamCreateWithFlags(&g_pipe.out, cudaStreamNonBlocking));
+        BSM_CUDA(cudaStreamCreateWithFlags(&g_pipe.meta, cudaStreamNonBlocking));
         for (cudaEvent_t &e : g_pipe.ev) BSM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         g_pipe_device = g_rt.device;
     }

@@ -900,15 +900,24 @@ def main():
             rv, rc, rr = res[0].raw_parts()
             got_rows = csr_rows_dense(rv, rc, rr, chk_ids, r0, n, dtype)
             nnz_out = int(rr[-1])
+            # what actually crosses PCIe: values + row_index, and the columns either as usize values (8 B per entry) or — the default —
+            # as one keep-bit per output, expanded into col_index by host threads inside the call (csrc/pipeline.cu, ColumnExpand)
+            expand_threads = os.environ.get("BSM_PIPE_EXPAND_THREADS", "")
+            by_masks = expand_threads != "0"
+            col_bytes = ai["rows"] * ((n + 63) // 64) * 8 if by_masks else nnz_out * 8
             e2e = {"value": round(2.0 * nnz_total * n / te / 1e9, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": int(h2d),
-                   "d2h_bytes_per_step": int(nnz_out * (s + 8) + (ai["rows"] + 1) * 8), "ms_per_step": round(te * 1e3, 2), "steps": steps_e,
+                   "d2h_bytes_per_step": int(nnz_out * s + col_bytes + (ai["rows"] + 1) * 8), "ms_per_step": round(te * 1e3, 2), "steps": steps_e,
+                   "result_bytes_in_host_memory": int(nnz_out * (s + 8) + (ai["rows"] + 1) * 8),
+                   "columns_on_the_wire": ("row masks (1 bit per output), expanded by host threads inside the call"
+                                           + (f" (BSM_PIPE_EXPAND_THREADS={expand_threads})" if expand_threads else " (default: 8 threads)"))
+                   if by_masks else "usize values",
                    "result": "Csr (zero-dropped, usize indices) — the reference's return type", "result_nnz_rank0": nnz_out,
                    "parity": {"rows_checked": int(len(chk_ids)) * world, "bitwise": all_true(bitwise_equal(got_rows, want_rows)),
                               "checker": "CPU oracle; rows of the returned Csr densified (dropped zeros = 0)"},
                    "phases_ms_rank0": ph, "numa": numa, "pcie_probe": pcie,
                    "path": "Csr.mul_dense_csr_into -> bsm_mul_dense_host_into_*: the literal Csr::mul_dense (sparse.rs:426-446): host Csr + host Dense "
                            "columns in, zero-dropped host Csr out; pipeline = A up | B up in row chunks + transpose | per row block SpMM + count/scan/scatter | "
-                           "values + usize columns + row_index down; pinned host buffers"}
+                           "values + row masks + row_index down, col_index written by host threads from the masks; pinned host buffers"}
             del ov, oc, orow, res
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's CPU path on a bounded sample ------------------

@@ -591,6 +591,39 @@ def test_pipelined_literal_call_many_blocks_and_chunks(gpu, dtype, kind, monkeyp
     assert_bitwise(dense.to_rowmajor(), ref_numpy.mul_dense_rowmajor(v, ci, ri, b), f"dense twin {kind}")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("threads", ["0", "3"])
+def test_literal_call_columns_travel_as_row_masks(gpu, dtype, threads, monkeypatch):
+    """The literal call sends one keep-bit per output instead of a usize column and host threads expand the masks into col_index
+    (BSM_PIPE_EXPAND_THREADS; 0 = the device writes usize columns and they are copied). Full rows (one pattern copy), rows with a
+    dropped zero, empty rows, many blocks: the result must equal the oracle's field by field, with and without the masks."""
+    monkeypatch.setenv("BSM_PIPE_BLOCK_BYTES", "30000")
+    monkeypatch.setenv("BSM_PIPE_CHUNK_BYTES", "9000")
+    monkeypatch.setenv("BSM_PIPE_EXPAND_THREADS", threads)
+    rng = np.random.default_rng(5)
+    m, k, n = 4001, 900, 20
+    v, ci, ri = _runs_csr(rng, m, k, dtype, 12, empty_frac=0.0, band=True)   # every row has entries: full result rows ...
+    v = (np.round(v * 8) / 8).astype(dtype)
+    v[v == 0] = 0.125
+    b = random_dense(rng, k, n, dtype, exact=True)
+    b[b == 0] = 1.0
+    b[600:640, 7] = 0                                               # ... except where a window of B is zero in one column
+    drop = set(range(1000, 1100)) | {2500, 3999}                    # ... and in blocks with empty rows
+    parts = [(v[int(ri[r]):int(ri[r + 1])], ci[int(ri[r]):int(ri[r + 1])]) if r not in drop else (v[:0], ci[:0]) for r in range(m)]
+    v, ci = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    ri = np.concatenate([[0], np.cumsum([len(p[0]) for p in parts])]).astype(np.uint64)
+    a = host_csr((m, k), v, ci, ri)
+    rhs = Dense.from_data([b[:, c] for c in range(n)], dtype)
+    ref = OracleCsr.from_raw((m, k), v, ci, ri).mul_dense([b[:, c].copy() for c in range(n)])
+    full = np.diff(ref.row_index.astype(np.int64)) == n
+    assert 0.5 < full.mean() < 1.0                                  # most rows full, some not
+    ov, oc, orow = np.empty(m * n, dtype), np.full(m * n, 0xDEADBEEF, np.uint64), np.empty(m + 1, np.uint64)
+    out = a.mul_dense_csr_into(rhs, ov, oc, orow)
+    assert_bitwise(out.v, ref.v)
+    assert np.array_equal(out.col_index, ref.col_index) and np.array_equal(out.row_index, ref.row_index)
+    assert a.mul_dense(rhs) == out                                  # allocating form
+
+
 def test_literal_call_edge_shapes(gpu):
     """Empty rows at both ends, one column, zero columns, 1 x 1."""
     for (m, k, n) in ((7, 5, 0), (9, 4, 1), (3, 3, 2), (1, 1, 1)):   # (a 0-row Csr cannot be finalised in the reference: "big eek")
