@@ -608,6 +608,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:   # the literal call expands the result's row masks with host threads: N ranks share the host's cores
+        os.environ.setdefault("BSM_PIPE_EXPAND_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // (2 * world)))))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
