@@ -272,6 +272,14 @@ static int spmm_rowblock(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, con
         sh.G = 4;
         while ((uint32_t)sh.G < lanes) sh.G *= 2;
         sh.NT = 1;
+        // Two register tiles per lane on half as many lanes — the default for full-width 128-bit shapes of at least 8 lanes: one value
+        // read (LDS) then feeds twice as many products, and the kernel is bound by the instructions it issues per product (band x32 f32
+        // 0.283 -> 0.244 ms, x64 f64 1.15 -> 0.87 ms, x128 f32 0.96 -> 0.87 ms, bit-exact; profiles/r2_sweep_rowblock_tiles_*.jsonl).
+        // bsm_tuning.lanes_per_row = the natural lane count keeps one tile per lane.
+        if ((size_t)sh.V * s == 16 && n == (uint32_t)(sh.V * sh.G) && sh.G >= 8 && (tn.lanes_per_row <= 0 || tn.lanes_per_row * 2 == sh.G)) {
+            sh.G /= 2;
+            sh.NT = 2;
+        }
         if (passes == 0) launch_info().col_tile = (int)n;
         RowBlockParams p{};
         p.row_ptr = a->row_ptr;

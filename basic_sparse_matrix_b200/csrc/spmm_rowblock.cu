@@ -44,9 +44,12 @@ __global__ void rowblock_probe_kernel(const uint32_t *__restrict__ row_ptr, cons
 // contiguous piece of the value array: a single TMA bulk copy, cp.async.bulk -> UBLKCP, completing on the warp's
 // mbarrier) + the mbarriers. The value reads are then warp-broadcast LDS instead of scattered global loads.
 // FUSED: the opt-in BSM_TUNE_FUSED arithmetic (one FMA per product; tolerance-level agreement with the reference)
-template <typename T, int V, int G, int RB, bool FULLN, bool FUSED>
-__global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(const RowBlockParams p)
+// NT: register tiles per lane (tile t holds the columns t*G*V + gl*V ...): with two tiles a lane's value read feeds twice as many
+// products (the kernel is bound by the instructions it issues per product; full-width shapes only)
+template <typename T, int V, int G, int RB, bool FULLN, bool FUSED, int NT = 1>
+__global__ void __launch_bounds__(256, (RB >= 8 || NT > 1) ? 2 : 3) spmm_rowblock_kernel(const RowBlockParams p)
 {
+    static_assert(NT == 1 || FULLN, "several tiles per lane: full-width shapes only");
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int RPP = 32 / G;                  // lane groups (row blocks) per warp
     constexpr uint32_t WR = RPP * RB;            // rows per warp block
@@ -107,9 +110,11 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
             }
         }
         if (jb <= ja) ja = jb = jhi;   // no intersection: the predicated loop walks the whole union
-        Lane<T, V> acc[RB];
+        Lane<T, V> acc[RB][NT];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) acc[r].zero();   // T::default()  sparse.rs:434
+        for (int r = 0; r < RB; ++r)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[r][t].zero();   // T::default()  sparse.rs:434
         if (we > ws) {
             mbar_wait(bar, phase);   // the values have landed
             phase ^= 1u;
@@ -119,14 +124,19 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
         auto ragged = [&](uint32_t j0, uint32_t j1) {
             const char *brow = b_bytes + (size_t)j0 * ldb_bytes;
             for (uint32_t j = j0; j < j1; ++j, brow += ldb_bytes) {
-                Lane<T, V> b;
-                b.zero();
-                if (col_ok) b.template load<false>(reinterpret_cast<const T *>(brow), 0ull);
+                Lane<T, V> b[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    b[t].zero();
+                    if (col_ok) b[t].template load<false>(reinterpret_cast<const T *>(brow) + t * G * V, 0ull);
+                }
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
                     const uint32_t off = j - first[r];
                     if (off < len[r]) {   // row r stores column j, at entry base + off; ascending j = stored order
-                        axpy<FUSED, T, V>(va[base[r] + off], b.x, acc[r].x, negzero2);
+                        const T a = va[base[r] + off];
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) axpy<FUSED, T, V>(a, b[t].x, acc[r][t].x, negzero2);
                     }
                 }
             }
@@ -142,12 +152,17 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
                 const char *brow = b_bytes + (size_t)ja * ldb_bytes;
 #pragma unroll 4
                 for (uint32_t j = ja; j < jb; ++j, brow += ldb_bytes) {
-                    Lane<T, V> b;
-                    b.zero();
-                    if (col_ok) b.template load<false>(reinterpret_cast<const T *>(brow), 0ull);
+                    Lane<T, V> b[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        b[t].zero();
+                        if (col_ok) b[t].template load<false>(reinterpret_cast<const T *>(brow) + t * G * V, 0ull);
+                    }
 #pragma unroll
                     for (int r = 0; r < RB; ++r) {
-                        axpy<FUSED, T, V>(vrow[r][j], b.x, acc[r].x, negzero2);
+                        const T a = vrow[r][j];
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) axpy<FUSED, T, V>(a, b[t].x, acc[r][t].x, negzero2);
                     }
                 }
             }
@@ -155,7 +170,10 @@ __global__ void __launch_bounds__(256, RB >= 8 ? 2 : 3) spmm_rowblock_kernel(con
         }
 #pragma unroll
         for (int r = 0; r < RB; ++r)
-            if (row0 + r < p.rows && col_ok) acc[r].store(reinterpret_cast<T *>(c_bytes + (size_t)(row0 + r) * ldc_bytes), streaming);
+            if (row0 + r < p.rows && col_ok) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) acc[r][t].store(reinterpret_cast<T *>(c_bytes + (size_t)(row0 + r) * ldc_bytes) + t * G * V, streaming);
+            }
     }
 }
 
@@ -192,6 +210,24 @@ template <typename T, int V, int G> static const void *rowblock_ptr(bool fulln, 
     return fulln ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, true, false>)
                  : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, false, false>);
 }
+// two register tiles per lane: full-width 128-bit shapes, blocks of 4 rows (four tiles spill at 128 registers and measured slower:
+// band x64 f64 0.87 -> 1.18 ms, x128 f32 0.87 -> 1.08 ms)
+template <typename T, int V, int G, int NT> static const void *rowblock_tiles_ptr(bool fused)
+{
+    return fused ? reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, true, true, NT>)
+                 : reinterpret_cast<const void *>(&spmm_rowblock_kernel<T, V, G, 4, true, false, NT>);
+}
+template <typename T, int V> static const void *rowblock_select_tiles(int G, int NT, bool fused)
+{
+    if constexpr (V * sizeof(T) == 16) {
+        if (NT == 2) switch (G) {
+                case 16: return rowblock_tiles_ptr<T, V, 16, 2>(fused);
+                case 8: return rowblock_tiles_ptr<T, V, 8, 2>(fused);
+                case 4: return rowblock_tiles_ptr<T, V, 4, 2>(fused);
+            }
+    }
+    return nullptr;
+}
 template <typename T, int V> static const void *rowblock_select_g(int G, bool fulln, int rb, bool fused)
 {
     switch (G) {
@@ -206,14 +242,19 @@ template <typename T, int V> static const void *rowblock_select_g(int G, bool fu
 int launch_spmm_rowblock(int dtype, Shape sh, const RowBlockParams &p_in, int rb, uint64_t max_row_nnz, int sm_count, size_t smem_max, cudaStream_t stream,
                          int *grid_out, int *block_out, int *smem_out, int *rb_out)
 {
-    if (sh.NT != 1) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rowblock: one register tile per lane only");
-    const bool fulln = p_in.n == (uint32_t)(sh.V * sh.G);
+    if (sh.NT != 1 && sh.NT != 2) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rowblock: one or two register tiles per lane");
+    const bool fulln = p_in.n == (uint32_t)(sh.V * sh.G * sh.NT);
+    if (sh.NT > 1 && !fulln) return fail(BSM_ERR_NOT_SUPPORTED, "spmm_rowblock: several register tiles per lane exist for full-width shapes only");
     const void *k = nullptr;
     const bool fused = (p_in.flags & BSM_TUNE_FUSED) != 0;
     if (rb != 4 && rb != 8) return fail(BSM_ERR_INVALID_ARGUMENT, "spmm_rowblock: 4 or 8 rows per block");
     if (rb == 8 && !(sh.G == 32 && sh.V * dtype_size(dtype) == 16)) rb = 4;   // blocks of 8 rows: full-warp 128-bit shapes only
+    if (sh.NT > 1) rb = 4;
     if (rb_out) *rb_out = rb;
-    if (dtype == BSM_F64) {
+    if (sh.NT > 1) {
+        if (dtype == BSM_F64 && sh.V == 2) k = rowblock_select_tiles<double, 2>(sh.G, sh.NT, fused);
+        if (dtype == BSM_F32 && sh.V == 4) k = rowblock_select_tiles<float, 4>(sh.G, sh.NT, fused);
+    } else if (dtype == BSM_F64) {
         if (sh.V == 1) k = rowblock_select_g<double, 1>(sh.G, fulln, rb, fused);
         if (sh.V == 2) k = rowblock_select_g<double, 2>(sh.G, fulln, rb, fused);
     } else {

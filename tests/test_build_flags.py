@@ -45,8 +45,8 @@ def sass():
 
 
 def is_fused_rowblock(name):
-    # spmm_rowblock_kernel<T, V, G, RB, FULLN, FUSED>: the mangled name ends ...Lb<FULLN>ELb<FUSED>EEEv...
-    return "spmm_rowblock_kernel" in name and re.search(r"Lb[01]ELb1EEEv", name) is not None
+    # spmm_rowblock_kernel<T, V, G, RB, FULLN, FUSED, NT>: the mangled name ends ...Lb<FULLN>ELb<FUSED>ELi<NT>EEEv...
+    return "spmm_rowblock_kernel" in name and re.search(r"Lb[01]ELb1ELi\dEEEv", name) is not None
 
 
 def test_no_fused_multiply_add_in_the_bit_exact_kernels(sass):

@@ -303,6 +303,19 @@ def test_rowblock_bitwise(gpu, dtype):
             assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), f"rowblock m={m} n={n} band={band}")
         got, _ = gpu_product(gpu, (m, k), v, ci, ri, random_dense(np.random.default_rng(1), k, 64, dtype), "rowblock", col_tile=16)
         assert_bitwise(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, random_dense(np.random.default_rng(1), k, 64, dtype)), "rowblock col_tile")
+        # full-width 128-bit shapes: two register tiles per lane on half the lanes by default, one tile per lane on request
+        per16 = 16 // np.dtype(dtype).itemsize
+        for lanes in (8, 16, 32):
+            n = per16 * lanes
+            b = random_dense(rng, k, n, dtype)
+            want = ref_numpy.mul_dense_rowmajor(v, ci, ri, b)
+            got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "rowblock")
+            assert (info["lanes_per_row"], info["reg_tiles"]) == (lanes // 2, 2), info
+            assert_bitwise(got, want, f"rowblock two tiles m={m} n={n}")
+            for rb in (4, 8):
+                got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "rowblock", lanes_per_row=lanes, rows_per_slice=rb)
+                assert (info["lanes_per_row"], info["reg_tiles"]) == (lanes, 1), info
+                assert_bitwise(got, want, f"rowblock one tile m={m} n={n} rb={rb}")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -318,10 +331,10 @@ def test_rowblock_fused_is_within_tolerance(gpu, dtype):
     for lanes in (8, 32):
         n = per16 * lanes
         b = random_dense(rng, k, n, dtype)
-        for rb in (4, 8):
-            got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "rowblock", flags=fused, rows_per_slice=rb)
-            assert info["algo"] == _lib.ALGO_ROWBLOCK
-            assert_tolerance(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), ref_numpy.abs_product_sum(v, ci, ri, b), TOL[dtype], f"fused n={n} rb={rb}")
+        for tune in (dict(rows_per_slice=4, lanes_per_row=lanes), dict(rows_per_slice=8, lanes_per_row=lanes), dict()):   # one tile per lane (4 / 8 rows), two tiles
+            got, info = gpu_product(gpu, (m, k), v, ci, ri, b, "rowblock", flags=fused, **tune)
+            assert info["algo"] == _lib.ALGO_ROWBLOCK and info["reg_tiles"] == (1 if tune else 2)
+            assert_tolerance(got, ref_numpy.mul_dense_rowmajor(v, ci, ri, b), ref_numpy.abs_product_sum(v, ci, ri, b), TOL[dtype], f"fused n={n} {tune}")
         ve = (np.round(v * 8) / 8).astype(dtype)
         be = random_dense(rng, k, n, dtype, exact=True)
         got, _ = gpu_product(gpu, (m, k), ve, ci, ri, be, "rowblock", flags=fused)
