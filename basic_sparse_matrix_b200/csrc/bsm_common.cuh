@@ -208,14 +208,6 @@ __device__ __forceinline__ float4 ldg_hint(const float4 *p, uint64_t pol)
                  : "l"(p), "l"(pol));
     return v;
 }
-// L2 prefetch of `bytes` (multiple of 16) at a 16-byte aligned global address: one TMA bulk prefetch (SASS: UBLKPF), no
-// destination, no completion to wait for
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes));
-}
-__device__ __forceinline__ void line_prefetch_l2(const void *src_gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(src_gmem)); }
-
 __device__ __forceinline__ uint64_t l2_policy_evict_last()
 {
     uint64_t pol;

@@ -2,7 +2,6 @@
 // and with what geometry. Replaces the call Csr::mul_dense, /root/reference/src/sparse.rs:426-446.
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 #include <string>
 
 #include "bsm_internal.h"
@@ -58,16 +57,6 @@ static int spmm_vector(const bsm_csr *a, const bsm_dense *b, bsm_dense *c, const
         const Shape sh = plan.sh;
         const int flavour = plan.flavour, nw = plan.nw;
         const size_t smem = plan.smem;
-        // EXPERIMENT: BSM_EXPERIMENT_PREFETCH=<mode bits> (RowParams::pf_mode) on the flat-stream, staged shapes
-        if (const char *e = getenv("BSM_EXPERIMENT_PREFETCH")) {
-            const int mode = atoi(e);
-            const uint64_t row_bytes = (uint64_t)n * s;
-            if (mode > 0 && (sh.G == 32 || sh.NT > 1) && flavour >= 0 && plan.stages >= 2 && row_bytes % 16 == 0 && (b->ld * s) % 16 == 0 &&
-                ((uintptr_t)p.B % 16) == 0) {
-                p.pf_mode = (uint32_t)mode;
-                p.pf_bytes = (uint32_t)row_bytes;
-            }
-        }
         p.R = plan.R;
         p.P = plan.P;
         p.stages = plan.stages;

@@ -28,11 +28,6 @@ struct RowParams {
     uint32_t cap;        // staged entries per slice (multiple of 4)
     uint32_t stages;     // TMA ring depth per warp
     uint32_t flags;      // BSM_TUNE_*
-    uint32_t pf_mode;    // L2 prefetch of the B row of every row's LAST stored entry (the first touch of a B row when a stencil
-                         // matrix is swept in row order): 0 = off; bit 0 = the rows of the slice being started, bit 1 = the rows
-                         // of the NEXT slice (its stage has landed), bit 2 = per 128-byte line from all lanes instead of one bulk
-                         // prefetch per row
-    uint32_t pf_bytes;   // bytes of one B row of this pass (multiple of 16)
     uint32_t n_peers;    // scatter variant: further destinations of every C row (0 = none)
     char *peers[7];      // their C pointers, offset like C (first column of the pass, this rank's first row)
 };

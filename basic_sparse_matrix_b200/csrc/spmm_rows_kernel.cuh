@@ -218,28 +218,6 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
         char *__restrict__ c_bytes = reinterpret_cast<char *>(static_cast<T *>(p.C) + gl * V);
         const bool streaming = (p.flags & BSM_TUNE_C_STREAMING) != 0;
 
-        // L2 prefetch of the B rows the LAST stored entries of a staged slice's rows will gather (p.pf_mode). Swept in row order, a
-        // stencil matrix touches B row j for the first time through the last entry of row j - plane: that gather is the one
-        // DRAM-latency load of a row, and it sits at the head of an in-order window. One site per slice, outside the entry loop.
-        auto prefetch_last_entries = [&](const unsigned char *st2, uint32_t row0_2, uint32_t nr2) {
-            const uint32_t *rp2 = reinterpret_cast<const uint32_t *>(st2 + L.rp_off) + (row0_2 & 3u);
-            const uint32_t *ci2 = reinterpret_cast<const uint32_t *>(st2 + L.idx_off) - (rp2[0] & ~3u);
-            const char *bb = static_cast<const char *>(p.B);
-            const uint32_t ldb_b = p.ldb * (uint32_t)sizeof(T);
-            if (p.pf_mode & 4u) {
-                const uint32_t lpr = (p.pf_bytes + 127u) >> 7;
-                for (uint32_t idx = lane; idx < nr2 * lpr; idx += 32u) {
-                    const uint32_t r = idx / lpr, ln = idx - r * lpr, e = rp2[r + 1];
-                    if (e > rp2[r]) line_prefetch_l2(bb + (size_t)ci2[e - 1] * ldb_b + ln * 128u);
-                }
-            } else if (lane == 0) {
-                for (uint32_t r = 0; r < nr2; ++r) {
-                    const uint32_t e = rp2[r + 1];
-                    if (e > rp2[r]) bulk_prefetch_l2(bb + (size_t)ci2[e - 1] * ldb_b, p.pf_bytes);
-                }
-            }
-        };
-
         for (uint32_t i = 0; i < my_slices; ++i) {
             __syncwarp();   // every lane is done reading the stage that is refilled next
             if (lane == 0 && i + p.stages - 1 < my_slices) issue(i + p.stages - 1);
@@ -254,21 +232,6 @@ __global__ void __launch_bounds__(MAXT, MINB) spmm_rows_kernel(const RowParams p
 
                 const unsigned char *st = ring + (size_t)stage * L.stage_bytes;
                 const uint32_t *rp = reinterpret_cast<const uint32_t *>(st + L.rp_off) + (row0 & 3u);
-                if constexpr (STAGED) {
-                    if (p.pf_mode) {
-                        if ((p.pf_mode & 1u) || i == 0) prefetch_last_entries(st, row0, nr);
-                        if ((p.pf_mode & 2u) && i + 1 < my_slices) {
-                            uint64_t r0n;
-                            uint32_t nrn;
-                            slice_pos(i + 1, r0n, nrn);
-                            if (nrn) {
-                                const uint32_t sn = (i + 1) % p.stages;
-                                mbar_wait(&full_bar[sn], ((i + 1) / p.stages) & 1u);   // issued two slices ago: has landed
-                                prefetch_last_entries(ring + (size_t)sn * L.stage_bytes, (uint32_t)r0n, nrn);
-                            }
-                        }
-                    }
-                }
                 if constexpr (STAGED)
                     process_slice<T, V, G, NT, FULLN, U, VECA, MULTI, FLAT>(p, rp, reinterpret_cast<const uint32_t *>(st + L.idx_off),
                                                                 reinterpret_cast<const T *>(st + L.vals_off), rp[0] & ~3u, row0, nr, b_bytes,

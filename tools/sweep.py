@@ -68,11 +68,6 @@ def main():
     with torch.cuda.stream(stream):
         for pt in args.points.split(";"):
             kw = {k: int(v, 0) for k, v in (kv.split("=") for kv in pt.split(",") if kv)}
-            pf = kw.pop("pf", 0)   # experiment knob of the vector kernel (csrc/dispatch.cu), read per call
-            if pf:
-                os.environ["BSM_EXPERIMENT_PREFETCH"] = str(pf)
-            else:
-                os.environ.pop("BSM_EXPERIMENT_PREFETCH", None)
             tuning = gpu.make_tuning(kw.pop("algo", args.algo), **kw)
             try:
                 total_ms, per = bench.time_device_steps(torch, A, B, C, args.steps, args.warmup, tuning)
