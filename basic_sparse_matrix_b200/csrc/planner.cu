@@ -143,6 +143,10 @@ static uint32_t pick_rows_per_warp(const MatrixFacts &m, const DeviceFacts &dev,
         P = best_p ? best_p : R;
         if (m.rows / ((uint64_t)nw * P) < (uint64_t)dev.sm_count) P = R;
     }
+    // 32- and 64-byte output rows on a stencil matrix: half / a quarter of a line per warp (x8 f64 0.951 -> 0.927 ms, x4 f64
+    // 0.660 -> 0.640 ms, profiles/r2_sweep_narrow_final_*.jsonl: these shapes are bound by L1 wavefronts, not by the sharing of
+    // neighbouring lines between the warps of a CTA, and shorter runs balance better)
+    if (tn.rows_per_warp <= 0 && sh.NT == 1 && (sh.G == 2 || sh.G == 4) && m.row_stride >= 2 * R && P == m.row_stride) P = std::max(R, P / (sh.G == 2 ? 4u : 2u));
     // flat-stream shapes take any P >= R (the last slice of a line may be short; the row_ptr windows are realigned in
     // the kernel); the row-by-row narrow shapes keep whole slices
     if (sh.G == 32 || sh.NT > 1) return std::max(R, P);

@@ -56,7 +56,7 @@ def test_64_byte_rows_walk_flat_streams_on_short_regular_rows(dtype, n):
     # four 128-bit lanes per row, 8 rows side by side, each lane group one flat entry stream over 8 rows of a 64-row slice
     p = plan(dtype, L3D["rows"], L3D["nnz"], L3D["max_row"], 256, n)
     assert (p["lanes_per_row"], p["reg_tiles"], p["reg_flavour"]) == (4, 1, 9)
-    assert (p["rows_per_slice"], p["rows_per_warp"], p["stages"], p["block"]) == (64, 256, 2 if dtype == F64 else 3, 512)
+    assert (p["rows_per_slice"], p["rows_per_warp"], p["stages"], p["block"]) == (64, 128, 2 if dtype == F64 else 3, 512)   # half a line per warp
     # long or uneven rows stay row by row; so do two-lane shapes
     assert plan(dtype, 1 << 20, 68_156_384, 65, 0, n)["reg_flavour"] == 1
     assert plan(dtype, L3D["rows"], L3D["nnz"], 60, 0, n)["reg_flavour"] == 1
