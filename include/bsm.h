@@ -247,7 +247,10 @@ int bsm_backward_substitution(const bsm_csr *l_star, const bsm_dense *y, bsm_den
  * max(0, r-hb) .. r (diagonal last) / r .. min(n-1, r+hb) (diagonal first), what cholesky_decomp and transpose() produce for a
  * band matrix (sparse.rs:682-714, 296-318) — else -1. Proper band factors of half-bandwidth 8, 16 or 32 with at least 4 hb rows
  * run a specialised kernel (one solver warp, no hand-overs between warps; same arithmetic, same bits); everything else the general
- * one. Either pointer may be NULL. */
+ * one (environment: BSM_SOLVE_GENERAL=1 forces the general kernel — the tests compare the two). The band kernels divide f32 by a
+ * shortcut that is the correctly rounded quotient while numerators stay in [2^-90, 2^90) (zeros included) and divisors in
+ * [2^-30, 2^30); when an operand leaves these ranges (infinity, NaN, subnormal, a solution that decays towards zero) the call
+ * discards the result and runs the general kernel: slower, same bits. Either pointer may be NULL. */
 int bsm_csr_band_structure(const bsm_csr *a, int32_t *lower_hb, int32_t *upper_hb);
 
 /* Host-to-host convenience = the literal reference call: uploads A and B, multiplies, compacts
@@ -268,8 +271,13 @@ int bsm_mul_dense_host_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const flo
  * bench.py times end to end with pinned arrays. rows * rhs_cols entries always suffice; too small a capacity fails
  * with BSM_ERR_INVALID_ARGUMENT (nothing useful is left in the arrays). The call is pipelined: B travels host -> device
  * in chunks of rows, each block of output rows is multiplied as soon as the B rows its columns reach have landed, and
- * its zero-dropped entries (values + usize columns + its row_index piece) travel device -> host while the next block
- * is computed. Use pinned host memory for the copies to overlap. */
+ * its zero-dropped entries travel device -> host while the next block is computed: the values and the row_index piece as
+ * they are, the column indices as one keep-bit per output, which a few threads inside the call expand into out_col_index
+ * (a full row — the normal case of Csr x Dense — is the pattern 0 .. rhs_cols-1). The arrays hold exactly what the reference's
+ * insert / finalise produce. Use pinned host memory for the copies to overlap.
+ * Environment: BSM_PIPE_EXPAND_THREADS = expansion threads (default 8, at most half of the hardware threads; 0 = usize
+ * columns are written on the device and copied, 8 bytes per entry); BSM_PIPE_EXPAND_NT=0 = plain instead of non-temporal
+ * stores; BSM_PIPE_BLOCK_BYTES / BSM_PIPE_CHUNK_BYTES = sizes of the row blocks / B chunks (tests). */
 int bsm_mul_dense_host_into_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v,
                                 const uint64_t *col_index, const uint64_t *row_index,
                                 uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,
