@@ -193,6 +193,14 @@ impl<T: GpuScalar> DeviceCsr<T> {
         check(unsafe { ffi::bsm_backward_substitution(self.h, y.h, x.h) })?;
         Ok(x)
     }
+    /// Half-bandwidths `(lower, upper)` when the matrix is a proper lower / upper band factor (what `cholesky_decomp` and
+    /// `transpose` return for a band matrix): such factors run the specialised substitution kernels. `None` otherwise.
+    pub fn band_structure(&self) -> Result<(Option<usize>, Option<usize>), GpuError> {
+        let (mut lo, mut up) = (-1i32, -1i32);
+        check(unsafe { ffi::bsm_csr_band_structure(self.h, &mut lo, &mut up) })?;
+        let opt = |v: i32| if v >= 0 { Some(v as usize) } else { None };
+        Ok((opt(lo), opt(up)))
+    }
 }
 
 /// nnz-balanced contiguous row split for the row-partitioned multi-GPU path (B replicated).
