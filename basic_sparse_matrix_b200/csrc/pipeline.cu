@@ -314,7 +314,10 @@ template <typename T> int host_product(const HostProduct<T> &q)
     T *bwin = nullptr, *cdev = nullptr, *stage_in[2] = {}, *stage_out[2] = {}, *vals_st[2] = {};
     uint64_t *cols_st[2] = {}, *rp64[2] = {}, *masks_st[2] = {}, *h_masks = nullptr;
     const uint64_t mwords = (n + 63) / 64;   // keep-bit words per result row
-    const bool by_masks = want_csr && expand.enabled();   // columns travel as row masks, expanded by host threads
+    // columns travel as row masks, expanded by host threads — for results large enough to pay for starting the threads (a small
+    // product is launch-bound: the reference's own bench shape, 10^4 outputs, went from 1.9 to 3.5 ms with them)
+    const uint64_t min_entries = getenv("BSM_PIPE_EXPAND_MIN_ENTRIES") ? env_bytes("BSM_PIPE_EXPAND_MIN_ENTRIES") : (4ull << 20);
+    const bool by_masks = want_csr && expand.enabled() && rows * n >= min_entries;
     uint32_t *counts[2] = {}, *blk_range = nullptr;
     unsigned long long *tot = nullptr, *h_tot = nullptr;
     uint32_t *h_range = nullptr;

@@ -277,7 +277,9 @@ int bsm_mul_dense_host_f32(uint64_t rows, uint64_t cols, uint64_t nnz, const flo
  * insert / finalise produce. Use pinned host memory for the copies to overlap.
  * Environment: BSM_PIPE_EXPAND_THREADS = expansion threads (default 8, at most half of the hardware threads; 0 = usize
  * columns are written on the device and copied, 8 bytes per entry); BSM_PIPE_EXPAND_NT=0 = plain instead of non-temporal
- * stores; BSM_PIPE_BLOCK_BYTES / BSM_PIPE_CHUNK_BYTES = sizes of the row blocks / B chunks (tests). */
+ * stores; BSM_PIPE_EXPAND_MIN_ENTRIES = smallest result (rows x rhs_cols, default 4 Mi) that takes the masks — smaller
+ * products are launch-bound and copy their usize columns; BSM_PIPE_BLOCK_BYTES / BSM_PIPE_CHUNK_BYTES = sizes of the row
+ * blocks / B chunks (tests). */
 int bsm_mul_dense_host_into_f64(uint64_t rows, uint64_t cols, uint64_t nnz, const double *v,
                                 const uint64_t *col_index, const uint64_t *row_index,
                                 uint64_t row_index_len, uint64_t rhs_rows, uint64_t rhs_cols,

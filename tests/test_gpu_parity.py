@@ -613,6 +613,7 @@ def test_literal_call_columns_travel_as_row_masks(gpu, dtype, threads, monkeypat
     monkeypatch.setenv("BSM_PIPE_BLOCK_BYTES", "30000")
     monkeypatch.setenv("BSM_PIPE_CHUNK_BYTES", "9000")
     monkeypatch.setenv("BSM_PIPE_EXPAND_THREADS", threads)
+    monkeypatch.setenv("BSM_PIPE_EXPAND_MIN_ENTRIES", "0")         # (small results skip the masks by default)
     rng = np.random.default_rng(5)
     m, k, n = 4001, 900, 20
     v, ci, ri = _runs_csr(rng, m, k, dtype, 12, empty_frac=0.0, band=True)   # every row has entries: full result rows ...
