@@ -90,5 +90,5 @@ def test_spmm_kernels_use_tma_bulk_copies_and_wide_loads(sass):
 
 def test_instantiation_table_stays_bounded(sass):
     kernels, _ = sass
-    assert len(kernels) < 340, len(kernels)
-    assert os.path.getsize(_lib.LIB_PATH) < 20 * 1024 * 1024
+    assert len(kernels) < 360, len(kernels)   # 337 today: 308 SpMM / conversion / generator kernels + 12 band substitution + 12 two-tile row-block + ...
+    assert os.path.getsize(_lib.LIB_PATH) < 22 * 1024 * 1024   # 19.7 MB today, line info included
