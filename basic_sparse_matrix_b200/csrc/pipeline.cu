@@ -209,8 +209,21 @@ public:
             for (uint64_t r = 0; r < rows; r += step)
                 jobs_.push_back(Job{landed, masks + r * words, row_index + r, col_index, std::min(step, rows - r), n, words});
         }
-        if (threads_.empty())
-            for (int t = 0; t < want_; ++t) threads_.emplace_back([this] { work(); });
+        if (threads_.empty()) {
+            try {
+                for (int t = 0; t < want_; ++t) threads_.emplace_back([this] { work(); });
+            } catch (...) {   // no thread could be started (resource limits): nothing may throw through the C ABI
+            }
+        }
+        if (threads_.empty()) {   // expand on the calling thread: slower, same result
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                closing_ = true;
+            }
+            work();
+            closing_ = false;
+            return;
+        }
         cv_.notify_all();
     }
     // everything issued so far is done when this returns
