@@ -7,10 +7,11 @@ library ``lib/libbsm_b200.so`` (C ABI in ``include/bsm.h``); this package is its
 of the reference interface.  No CPU fallback exists.
 """
 from .dense import Dense
+from .dense_static import DenseS
 from .sparse import Csr, CsrEntry
 from .util import GetDims, MatDim, MatErr, MatError
 
-__all__ = ["Csr", "CsrEntry", "Dense", "GetDims", "MatDim", "MatErr", "MatError", "gpu", "gen", "solve"]
+__all__ = ["Csr", "CsrEntry", "Dense", "DenseS", "GetDims", "MatDim", "MatErr", "MatError", "gpu", "gen", "solve"]
 
 
 def __getattr__(name):

@@ -200,6 +200,17 @@ class Csr(GetDims):
             L.bsm_host_free(orow)
         return Csr.from_raw_parts((self.dims.rows, rhs.col_count), rv, rc, rr)
 
+    def mul_dense_s(self, rhs, algo: str = "auto") -> "Csr":
+        """``Csr::mul_dense_s(&self, rhs:&DenseS<T,ROWS,COLS>) -> Result<Csr<T>,MatErr>`` (sparse.rs:448-466): the same
+        loop nest as ``mul_dense`` against the fixed-size operand, so the same GPU call.  The dimension check is against
+        the const parameter ``ROWS`` (sparse.rs:449) and the result has ``rhs.get_dims().cols`` columns (sparse.rs:450,453);
+        a ``DenseS`` whose recorded ``col_count`` exceeds ``COLS`` (dense_static.rs:21-35) is the reference's index panic,
+        here an ``IndexError`` from ``get_col``."""
+        if self.dims.cols != rhs.ROWS:
+            raise MatError(MatErr.IncorrectDimensions)
+        n = rhs.get_dims().cols
+        return self.mul_dense(Dense(n, rhs.ROWS, [rhs.get_col(c) for c in range(n)]), algo=algo)
+
     def mul_dense_csr_into(self, rhs: Dense, out_v: np.ndarray, out_col_index: np.ndarray, out_row_index: np.ndarray,
                            algo: str = "auto") -> "Csr":
         """The literal ``mul_dense`` into caller-provided result arrays (``bsm_mul_dense_host_into_*``): ``out_v`` /

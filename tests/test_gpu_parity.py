@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from helpers import assert_bitwise, assert_tolerance, random_csr, random_dense
-from basic_sparse_matrix_b200 import Csr, Dense, MatErr, MatError, _lib, gen
+from basic_sparse_matrix_b200 import Csr, Dense, DenseS, MatErr, MatError, _lib, gen
 from oracle import ref_numpy
 from oracle.ref_cpu import OracleCsr
 
@@ -53,6 +53,18 @@ def test_reference_kats(gpu, golden, dtype):
             assert output.get_nnz() == k["nnz"]
         for algo in ("vector", "merge"):
             assert s.mul_dense(d, algo=algo) == output_ref, (k["name"], algo)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_mul_dense_s_kat(gpu, golden, dtype):
+    """Csr::mul_dense_s (sparse.rs:448-466) on the test_dense_mul operands held as a DenseS<T,4,3>, as
+    tests/cpp/test_reference_kats.cpp does through the C++ mirror."""
+    k = golden["mul_dense"][0]
+    m = Csr.from_data(k["csr_rows"], dtype)
+    assert m.mul_dense_s(DenseS.from_data(k["dense_columns"], 4, 3, dtype)) == Csr.from_data(k["output_rows"], dtype)
+    with pytest.raises(MatError) as e:
+        m.mul_dense_s(DenseS.new_default(3, 3, dtype))
+    assert e.value.kind == MatErr.IncorrectDimensions
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -3,7 +3,7 @@ loud failure of the product path when no CUDA device is usable (no CPU fallback)
 import numpy as np
 import pytest
 
-from basic_sparse_matrix_b200 import Csr, Dense, MatDim, MatErr, MatError
+from basic_sparse_matrix_b200 import Csr, Dense, DenseS, MatDim, MatErr, MatError
 from basic_sparse_matrix_b200 import _lib
 
 
@@ -92,6 +92,47 @@ def test_dimension_error_is_raised_before_any_device_work():
     with pytest.raises(MatError) as e:
         Csr.from_data([[0, 0, 0, 0]] * 3).mul_vector(np.arange(5.0), out)   # sparse.rs:469-471
     assert e.value.kind == MatErr.IncorrectDimensions
+
+
+def test_dense_static_kats():
+    """The reference's own DenseS tests (dense_static.rs:74-96) and its from_data quirk (dims from the slices)."""
+    a = DenseS.new_default(7, 5, np.int32)                                  # DenseS::<i32,7,5>::new_default()
+    assert a == DenseS.from_data([[0] * 7] * 5, dtype=np.int32)
+    assert a.get_dims() == MatDim(rows=7, cols=5)
+    b = DenseS.from_data([[1, 2, 3], [4, 5, 6], [7, 8, 9]], 3, 3, np.int32)
+    assert b.get_col(2).tolist() == [7, 8, 9]
+    assert str(b) == "|    1    4    7|\n|    2    5    8|\n|    3    6    9|\n"
+    assert DenseS.new(2.5, 2, 3).data.tolist() == [[2.5, 2.5]] * 3
+    q = DenseS.from_data([[1, 2, 3], [4, 5, 6], [7, 8, 9]], 2, 2)           # window 2 x 2, dims 3 x 3 (dense_static.rs:22-33)
+    assert q.data.tolist() == [[1, 2], [4, 5]] and q.get_dims() == MatDim(rows=3, cols=3)
+    with pytest.raises(IndexError):
+        DenseS.from_data([[1, 2]], 3, 1)                                     # slice shorter than ROWS: the reference's panic
+    with pytest.raises(IndexError):
+        q.get_col(2)
+
+
+def test_mul_dense_s_front_end(golden, monkeypatch):
+    """Csr::mul_dense_s (sparse.rs:448-466): dimension check against ROWS before any device work, then the same call as
+    mul_dense with the DenseS columns.  The device call is replaced by the oracle HERE only to check which operand the
+    front-end hands over (the GPU KAT is tests/test_gpu_parity.py::test_mul_dense_s_kat)."""
+    from oracle.ref_cpu import OracleCsr
+    k = golden["mul_dense"][0]
+    m = Csr.from_data(k["csr_rows"])
+    with pytest.raises(MatError) as e:
+        m.mul_dense_s(DenseS.new_default(3, 3))                              # 4 columns against ROWS = 3
+    assert e.value.kind == MatErr.IncorrectDimensions
+    seen = {}
+
+    def fake_mul_dense(self, rhs, algo="auto"):
+        seen["dims"], seen["algo"] = rhs.get_dims(), algo
+        o = OracleCsr.from_data(np.array(k["csr_rows"], np.float64), np.float64).mul_dense([np.ascontiguousarray(c, np.float64) for c in rhs.data])
+        return Csr.from_raw_parts((self.dims.rows, rhs.col_count), o.v, o.col_index, o.row_index)
+
+    monkeypatch.setattr(Csr, "mul_dense", fake_mul_dense)
+    out = m.mul_dense_s(DenseS.from_data(k["dense_columns"], 4, 3), algo="vector")
+    assert out == Csr.from_data(k["output_rows"]) and seen == {"dims": MatDim(rows=4, cols=3), "algo": "vector"}
+    with pytest.raises(IndexError):                                          # col_count 3 > COLS 2: the reference's index panic
+        m.mul_dense_s(DenseS.from_data(k["dense_columns"], 4, 2))
 
 
 def test_integer_dtype_is_rejected_not_emulated():
