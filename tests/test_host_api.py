@@ -70,6 +70,40 @@ def test_host_csr_matches_oracle_construction():
     assert np.array_equal(h.row_index, o.row_index)
 
 
+def test_insert_sequences_match_the_oracle_property():
+    """Any sequence of inserts — rows out of order, gaps, zeros, rows beyond the declared dimensions — builds the same three arrays in
+    the Python mirror as in the C oracle (sparse.rs:222-250, 206-219), or fails the same way (finalise's panic, 212-214)."""
+    from hypothesis import given, settings, strategies as st
+    from oracle.ref_cpu import OracleCsr
+
+    entry = st.tuples(st.sampled_from([0.0, -0.0, 1.0, -2.5, 3.0, float("inf")]), st.integers(0, 9), st.integers(0, 7))
+
+    @settings(max_examples=200, deadline=None)
+    @given(rows=st.integers(1, 8), entries=st.lists(entry, max_size=24))
+    def check(rows, entries):
+        h, o = Csr.new((rows, 8)), OracleCsr.new((rows, 8), np.float64)
+        for v, r, c in entries:
+            h.insert(v, r, c)
+            o.insert(v, r, c)
+        try:
+            o.finalise()
+        except RuntimeError as e:
+            assert "big eek" in str(e)
+            with pytest.raises(RuntimeError):
+                h.finalise()
+            return
+        h.finalise()
+        assert np.array_equal(h.v.view(np.uint64), o.v.view(np.uint64))
+        assert np.array_equal(h.col_index, o.col_index) and np.array_equal(h.row_index, o.row_index)
+        assert h.get_nnz() == o.get_nnz()
+        with pytest.raises(MatError):
+            h.insert(1.0, 0, 0)                                              # MatrixFinalised on both sides
+        with pytest.raises(RuntimeError):
+            o.insert(1.0, 0, 0)
+
+    check()
+
+
 def test_get_row_compact():
     m = Csr.from_data([[8, 0, 2, 0, 0], [0, 0, 5, 0, 0], [0, 0, 0, 0, 0]])
     row = m.get_row_compact(0)
