@@ -14,7 +14,7 @@ fn main() {
         let obj = out.join(format!("{src}.o"));
         let status = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-                   "-Xcompiler", "-fPIC", "-Icsrc", "-c"])
+                   "-Xfatbin", "-compress-all", "-Xcompiler", "-fPIC", "-Icsrc", "-c"])
             .arg(format!("csrc/{src}"))
             .arg("-o").arg(&obj)
             .status()
